@@ -1,0 +1,111 @@
+"""ctypes binding of libbetazero_b200.so -- the only way this package computes anything.
+
+There is NO CPU fallback: if the CUDA library is missing and cannot be built, importing a
+compute path raises.  Device pointers are ``tensor.data_ptr()`` of CUDA tensors; the stream is
+``torch.cuda.current_stream().cuda_stream`` (PyTorch is plumbing: device memory and streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+ptr = C.c_void_p
+
+
+class BzTreePools(C.Structure):
+    """Mirror of ``bz_tree_pools`` (include/betazero_b200.h)."""
+
+    _fields_ = [
+        ("game", C.c_int32), ("board_size", C.c_int32), ("n_trees", C.c_int32), ("n_actions", C.c_int32),
+        ("edge_cap", C.c_int32), ("max_depth", C.c_int32), ("c_puct", C.c_float), ("reserved", C.c_int32),
+        ("root_me", ptr), ("root_opp", ptr), ("root_meta", ptr), ("edge_count", ptr), ("sim_count", ptr),
+        ("depth_sum", ptr), ("error", ptr),
+        ("edge_N", ptr), ("edge_W", ptr), ("edge_P", ptr), ("edge_meta", ptr), ("edge_me", ptr), ("edge_opp", ptr),
+        ("path", ptr), ("path_len", ptr), ("leaf_me", ptr), ("leaf_opp", ptr), ("leaf_mask", ptr),
+        ("leaf_status", ptr), ("leaf_value", ptr), ("leaf_planes", ptr),
+    ]
+
+
+# name -> argtypes; every function returns int.  Must list EVERY symbol of include/betazero_b200.h
+# (tests/test_abi.py cross-checks this table against the header).
+_I64, _INT, _U64, _F = C.c_int64, C.c_int, C.c_uint64, C.c_float
+_PP = C.POINTER(BzTreePools)
+SIGNATURES = {
+    "bz_abi_version": [],
+    "bz_error_string": [_INT],
+    "bz_reversi_init": [ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_reversi_legal_mask": [ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_reversi_apply": [ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_reversi_terminal": [ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_reversi_step_first_legal": [ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_reversi_planes": [ptr, ptr, ptr, _I64, ptr],
+    "bz_ttt_legal_mask": [ptr, ptr, ptr, _I64, ptr],
+    "bz_ttt_apply": [ptr, ptr, ptr, ptr, ptr, ptr, ptr, _I64, ptr],
+    "bz_ttt_terminal": [ptr, ptr, ptr, ptr, _I64, ptr],
+    "bz_mcts_reset": [_PP, ptr, ptr, ptr],
+    "bz_mcts_select": [_PP, ptr],
+    "bz_mcts_gather": [_PP, ptr],
+    "bz_mcts_expand_backup": [_PP, ptr, ptr, ptr],
+    "bz_mcts_step": [_PP, ptr, ptr, ptr],
+    "bz_mcts_root_policy": [_PP, ptr, ptr, ptr, ptr],
+    "bz_mcts_best_action": [_PP, ptr, ptr],
+    "bz_hash_eval": [ptr, ptr, _U64, _INT, ptr, ptr, _I64, ptr],
+    "bz_int32_microbench": [ptr, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],
+}
+
+
+class BzError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """dlopen the CUDA library, building it first if needed.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    try:
+        if _build.needs_build():
+            _build.build()
+    except Exception as e:  # nvcc missing on a box that received a prebuilt .so is fine
+        if not os.path.exists(path):
+            raise BzError(f"libbetazero_b200.so is missing and could not be built ({e}); "
+                          "there is no CPU fallback") from e
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == "bz_error_string" else C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().bz_error_string(rc)
+        raise BzError(f"{what or 'bz call'} failed: {msg.decode() if msg else rc} (code {rc})")
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t):
+    """device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise BzError("expected a CUDA tensor: the engine has no CPU path")
+    if not t.is_contiguous():
+        raise BzError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,126 @@
+// Bitboard rules for Reversi and tic-tac-toe, device side (sm_100a).
+//
+// Replaces the reference's grid + ray walk (src/reversi/game_logic/reversi_board.py:25-59,
+// src/tic_tac_toe/tic_tac_toe_board.py:20-43) with branch-free 64-bit shift fills.
+// bit = row*8 + col.  All functions are pure; one thread handles one board.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bz {
+
+constexpr uint64_t kNotEdgeCols = 0x7E7E7E7E7E7E7E7EULL;  // columns 1..6: horizontal/diagonal fills must not wrap rows
+
+// cells of a size x size board embedded in the 8x8 bit grid
+__host__ __device__ constexpr uint64_t cell_mask(int size) {
+    return size >= 8 ? ~0ULL : (size == 6 ? 0x00003F3F3F3F3F3FULL : (size == 4 ? 0x000000000F0F0F0FULL : 0ULL));
+}
+
+// start position, mover = +1 (X): X on the main diagonal of the centre 2x2 (reversi_board.py:9-11)
+__host__ __device__ constexpr uint64_t start_me(int size) {
+    return (1ULL << ((size / 2 - 1) * 9)) | (1ULL << ((size / 2) * 9));
+}
+__host__ __device__ constexpr uint64_t start_opp(int size) {
+    return (1ULL << ((size / 2 - 1) * 8 + size / 2)) | (1ULL << ((size / 2) * 8 + size / 2 - 1));
+}
+
+// Kogge-Stone fill of `gen` through `pro` in both senses of one axis (shift DIR), returning the
+// cells just past each filled run.  Runs are at most 6 long: 1 + 1 + 2 + 2 steps cover them.
+template <int DIR>
+__device__ __forceinline__ uint64_t axis_moves(uint64_t gen, uint64_t pro) {
+    uint64_t up = pro & (gen << DIR), dn = pro & (gen >> DIR);
+    up |= pro & (up << DIR);
+    dn |= pro & (dn >> DIR);
+    const uint64_t pu = pro & (pro << DIR), pd = pro & (pro >> DIR);
+    up |= pu & (up << (2 * DIR));
+    dn |= pd & (dn >> (2 * DIR));
+    up |= pu & (up << (2 * DIR));
+    dn |= pd & (dn >> (2 * DIR));
+    return (up << DIR) | (dn >> DIR);
+}
+
+// K1: all cells where ReversiBoard.is_valid_move(r, c, mover) holds (reversi_board.py:25-41).
+__device__ __forceinline__ uint64_t legal_mask(uint64_t me, uint64_t opp, uint64_t cells) {
+    const uint64_t inner = opp & kNotEdgeCols;
+    uint64_t m = axis_moves<1>(me, inner);
+    m |= axis_moves<8>(me, opp);
+    m |= axis_moves<7>(me, inner);
+    m |= axis_moves<9>(me, inner);
+    return m & ~(me | opp) & cells;
+}
+
+// discs flipped along one axis by a move on the single-bit board `x`
+template <int DIR>
+__device__ __forceinline__ uint64_t axis_flips(uint64_t x, uint64_t me, uint64_t pro) {
+    uint64_t up = pro & (x << DIR), dn = pro & (x >> DIR);
+    up |= pro & (up << DIR);
+    dn |= pro & (dn >> DIR);
+    const uint64_t pu = pro & (pro << DIR), pd = pro & (pro >> DIR);
+    up |= pu & (up << (2 * DIR));
+    dn |= pd & (dn >> (2 * DIR));
+    up |= pu & (up << (2 * DIR));
+    dn |= pd & (dn >> (2 * DIR));
+    // a run counts only if the cell just past it holds a mover disc (reversi_board.py:56)
+    const uint64_t fu = (me & (up << DIR)) ? up : 0ULL;
+    const uint64_t fd = (me & (dn >> DIR)) ? dn : 0ULL;
+    return fu | fd;
+}
+
+// K2 core: discs flipped by placing on bit `x` (reversi_board.py:49-58).  0 <=> no direction
+// brackets anything, which with an empty target cell is exactly "not is_valid_move".
+__device__ __forceinline__ uint64_t flips_for(uint64_t x, uint64_t me, uint64_t opp) {
+    const uint64_t inner = opp & kNotEdgeCols;
+    return axis_flips<1>(x, me, inner) | axis_flips<8>(x, me, opp) | axis_flips<7>(x, me, inner) |
+           axis_flips<9>(x, me, inner);
+}
+
+struct Applied {
+    uint64_t me, opp;  // next mover's view
+    bool ok;
+};
+
+// make_move + pass with the validity rules of bz_reversi_apply (see include/betazero_b200.h)
+__device__ __forceinline__ Applied apply_action(uint64_t me, uint64_t opp, unsigned action, uint64_t cells) {
+    Applied r;
+    if (action < 64u) {
+        const uint64_t x = 1ULL << action;
+        const uint64_t f = flips_for(x, me, opp);
+        r.ok = (x & ~(me | opp) & cells) != 0 && f != 0;
+        r.me = opp & ~f;
+        r.opp = me | x | f;
+    } else {
+        r.ok = action == 64u && legal_mask(me, opp, cells) == 0;
+        r.me = opp;
+        r.opp = me;
+    }
+    if (!r.ok) {
+        r.me = me;
+        r.opp = opp;
+    }
+    return r;
+}
+
+// apply an action already known to be legal (tree descent): no validity work
+__device__ __forceinline__ void apply_legal(uint64_t &me, uint64_t &opp, unsigned action) {
+    if (action < 64u) {
+        const uint64_t x = 1ULL << action;
+        const uint64_t f = flips_for(x, me, opp);
+        const uint64_t nm = opp & ~f;
+        opp = me | x | f;
+        me = nm;
+    } else {
+        const uint64_t t = me;
+        me = opp;
+        opp = t;
+    }
+}
+
+// ---- tic-tac-toe: 9-bit boards, bit = row*3 + col --------------------------------------------
+__device__ __forceinline__ bool ttt_has_line(unsigned b) {
+    // rows 0x007 0x038 0x1C0, columns 0x049 0x092 0x124, diagonals 0x111 0x054
+    return ((b & 0x007u) == 0x007u) | ((b & 0x038u) == 0x038u) | ((b & 0x1C0u) == 0x1C0u) |
+           ((b & 0x049u) == 0x049u) | ((b & 0x092u) == 0x092u) | ((b & 0x124u) == 0x124u) |
+           ((b & 0x111u) == 0x111u) | ((b & 0x054u) == 0x054u);
+}
+
+}  // namespace bz

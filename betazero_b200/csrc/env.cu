@@ -1,0 +1,344 @@
+// Lockstep bitboard environment kernels (K1-K4, K6) for sm_100a.
+//
+// One thread owns two consecutive boards of the SoA arrays and moves them with 128-bit
+// streaming loads/stores (fully coalesced: a warp touches 512 contiguous bytes per array).
+// The kernels are grid-stride with grids sized in multiples of the 148 SMs.  All arithmetic is
+// 64-bit integer shifts/logic: the kernels are INT32-issue bound, not HBM bound.
+#include "bitboard.cuh"
+#include "common.cuh"
+
+namespace bz {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSM = 4;  // 1024 threads/SM at <= 64 registers: the kernels are ILP-rich and INT-issue bound
+
+template <bool VEC>
+__device__ __forceinline__ void load2(const uint64_t *__restrict__ p, int64_t i, int64_t n, uint64_t &a, uint64_t &b) {
+    if (VEC && i + 1 < n) {
+        const ulonglong2 v = ld_stream_u64x2(p + i);
+        a = v.x;
+        b = v.y;
+    } else {
+        a = p[i];
+        b = (i + 1 < n) ? p[i + 1] : 0ULL;
+    }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store2(uint64_t *__restrict__ p, int64_t i, int64_t n, uint64_t a, uint64_t b) {
+    if (VEC && i + 1 < n) {
+        st_stream_u64x2(p + i, make_ulonglong2(a, b));
+    } else {
+        p[i] = a;
+        if (i + 1 < n) p[i + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) init_kernel(uint64_t *me, uint64_t *opp, int8_t *player, int64_t n, int size) {
+    const uint64_t m = start_me(size), o = start_opp(size);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        me[i] = m;
+        opp[i] = o;
+        if (player) player[i] = 1;
+    }
+}
+
+// K1 ------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    legal_mask_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, uint64_t *__restrict__ mask,
+                      int64_t n, uint64_t cells) {
+    const int64_t pairs = (n + 1) >> 1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = p << 1;
+        uint64_t m0, m1, o0, o1;
+        load2<VEC>(me, i, n, m0, m1);
+        load2<VEC>(opp, i, n, o0, o1);
+        store2<VEC>(mask, i, n, legal_mask(m0, o0, cells), legal_mask(m1, o1, cells));
+    }
+}
+
+// K2 ------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    apply_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, const uint8_t *__restrict__ action,
+                 uint64_t *__restrict__ me_out, uint64_t *__restrict__ opp_out, uint8_t *__restrict__ err, int64_t n,
+                 uint64_t cells) {
+    const int64_t pairs = (n + 1) >> 1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = p << 1;
+        const bool two = i + 1 < n;
+        uint64_t m0, m1, o0, o1;
+        load2<VEC>(me, i, n, m0, m1);
+        load2<VEC>(opp, i, n, o0, o1);
+        const unsigned a0 = action[i], a1 = two ? action[i + 1] : 64u;
+        const Applied r0 = apply_action(m0, o0, a0, cells);
+        const Applied r1 = apply_action(m1, o1, a1, cells);
+        store2<VEC>(me_out, i, n, r0.me, r1.me);
+        store2<VEC>(opp_out, i, n, r0.opp, r1.opp);
+        if (err) {
+            err[i] = r0.ok ? 0 : 1;
+            if (two) err[i + 1] = r1.ok ? 0 : 1;
+        }
+    }
+}
+
+// K3 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void terminal_one(uint64_t m, uint64_t o, uint64_t cells, uint8_t *over, int8_t *win,
+                                             uint8_t *cm, uint8_t *co, int64_t i) {
+    const int a = __popcll(m), b = __popcll(o);
+    if (over) over[i] = (legal_mask(m, o, cells) | legal_mask(o, m, cells)) == 0 ? 1 : 0;
+    if (win) win[i] = (int8_t)((a > b) - (a < b));
+    if (cm) cm[i] = (uint8_t)a;
+    if (co) co[i] = (uint8_t)b;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    terminal_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, uint8_t *__restrict__ over,
+                    int8_t *__restrict__ win, uint8_t *__restrict__ cm, uint8_t *__restrict__ co, int64_t n,
+                    uint64_t cells) {
+    const int64_t pairs = (n + 1) >> 1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = p << 1;
+        uint64_t m0, m1, o0, o1;
+        load2<VEC>(me, i, n, m0, m1);
+        load2<VEC>(opp, i, n, o0, o1);
+        terminal_one(m0, o0, cells, over, win, cm, co, i);
+        if (i + 1 < n) terminal_one(m1, o1, cells, over, win, cm, co, i + 1);
+    }
+}
+
+// K1 + K2 fused: one ply with the "first legal move" player --------------------------------------
+__device__ __forceinline__ void step_one(uint64_t &m, uint64_t &o, uint64_t cells, uint64_t &mask, unsigned &act) {
+    mask = legal_mask(m, o, cells);
+    act = mask ? (unsigned)(__ffsll((long long)mask) - 1) : 64u;
+    apply_legal(m, o, act);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    step_first_legal_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp,
+                            uint64_t *__restrict__ mask_out, uint8_t *__restrict__ action_out,
+                            uint64_t *__restrict__ me_out, uint64_t *__restrict__ opp_out, int64_t n, uint64_t cells) {
+    const int64_t pairs = (n + 1) >> 1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = p << 1;
+        uint64_t m0, m1, o0, o1, k0, k1;
+        unsigned a0, a1;
+        load2<VEC>(me, i, n, m0, m1);
+        load2<VEC>(opp, i, n, o0, o1);
+        step_one(m0, o0, cells, k0, a0);
+        step_one(m1, o1, cells, k1, a1);
+        if (mask_out) store2<VEC>(mask_out, i, n, k0, k1);
+        store2<VEC>(me_out, i, n, m0, m1);
+        store2<VEC>(opp_out, i, n, o0, o1);
+        if (action_out) {
+            action_out[i] = (uint8_t)a0;
+            if (i + 1 < n) action_out[i + 1] = (uint8_t)a1;
+        }
+    }
+}
+
+// K6 stand-alone: 16 threads per board, each writes one 8-cell row of one plane as 16 bytes -------
+__device__ __forceinline__ uint4 row_to_bf16x8(unsigned row8) {
+    // bf16 1.0 = 0x3F80; cell c of the row goes to element c
+    uint4 v;
+    v.x = ((row8 & 1u) ? 0x3F80u : 0u) | ((row8 & 2u) ? 0x3F800000u : 0u);
+    v.y = ((row8 & 4u) ? 0x3F80u : 0u) | ((row8 & 8u) ? 0x3F800000u : 0u);
+    v.z = ((row8 & 16u) ? 0x3F80u : 0u) | ((row8 & 32u) ? 0x3F800000u : 0u);
+    v.w = ((row8 & 64u) ? 0x3F80u : 0u) | ((row8 & 128u) ? 0x3F800000u : 0u);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    planes_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, uint4 *__restrict__ planes, int64_t n) {
+    const int64_t chunks = n * 16;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < chunks; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g >> 4;
+        const int c = (int)(g & 15);
+        const uint64_t bits = (c & 8) ? opp[b] : me[b];
+        planes[g] = row_to_bf16x8((unsigned)(bits >> ((c & 7) * 8)) & 0xFFu);
+    }
+}
+
+// K4: tic-tac-toe ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ttt_mask_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ o,
+                                                           uint16_t *__restrict__ mask, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mask[i] = (uint16_t)(~(x[i] | o[i]) & 0x1FFu);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    ttt_apply_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ o, const uint8_t *__restrict__ action,
+                     const int8_t *__restrict__ player, uint16_t *__restrict__ xo, uint16_t *__restrict__ oo,
+                     uint8_t *__restrict__ err, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned xv = x[i], ov = o[i];
+        const unsigned a = action[i];
+        const unsigned bit = a < 9u ? (1u << a) : 0u;
+        const bool ok = bit != 0 && ((xv | ov) & bit) == 0;
+        if (ok) {
+            if (player[i] > 0) xv |= bit;
+            else ov |= bit;
+        }
+        xo[i] = (uint16_t)xv;
+        oo[i] = (uint16_t)ov;
+        if (err) err[i] = ok ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) ttt_terminal_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ o,
+                                                               uint8_t *__restrict__ over, int8_t *__restrict__ winner,
+                                                               int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned xv = x[i] & 0x1FFu, ov = o[i] & 0x1FFu;
+        int w = 2;  // Python None
+        if (ttt_has_line(xv)) w = 1;  // +1 is tested first (tic_tac_toe_board.py:32)
+        else if (ttt_has_line(ov)) w = -1;
+        else if ((xv | ov) == 0x1FFu) w = 0;
+        if (over) over[i] = w != 2;
+        if (winner) winner[i] = (int8_t)w;
+    }
+}
+
+// INT32 issue-rate microbenchmark ----------------------------------------------------------------
+// 8 independent chains of {SHF, LOP3, IADD3}: the instruction mix of the bitboard kernels.
+__global__ void __launch_bounds__(kThreads) int32_bench_kernel(uint32_t *sink, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const uint32_t k = blockIdx.x | 1u;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __funnelshift_l(a0, a1, 7) ^ (a0 & k);
+            a1 = __funnelshift_l(a1, a2, 9) ^ (a1 | k);
+            a2 = __funnelshift_l(a2, a3, 11) ^ (a2 & k);
+            a3 = __funnelshift_l(a3, a4, 13) ^ (a3 | k);
+            a4 = __funnelshift_l(a4, a5, 3) ^ (a4 & k);
+            a5 = __funnelshift_l(a5, a6, 5) ^ (a5 | k);
+            a6 = __funnelshift_l(a6, a7, 17) ^ (a6 & k);
+            a7 = __funnelshift_l(a7, a0, 19) ^ (a7 | k);
+        }
+    }
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0xDEADBEEFu) *sink = r;  // keeps the chains live without memory traffic
+}
+
+bool size_ok(int size) { return size == 4 || size == 6 || size == 8; }
+
+}  // namespace
+}  // namespace bz
+
+using namespace bz;
+
+extern "C" {
+
+int bz_abi_version(void) { return BZ_ABI_VERSION; }
+
+const char *bz_error_string(int code) {
+    if (code == BZ_OK) return "ok";
+    if (code == BZ_ERR_ARG) return "invalid argument";
+    if (code == BZ_ERR_UNALIGNED) return "pointer not aligned";
+    if (code <= -1000) return cudaGetErrorString((cudaError_t)(-code - 1000));
+    return "unknown error";
+}
+
+int bz_reversi_init(uint64_t *me, uint64_t *opp, int8_t *player, int64_t n, int size, bz_stream_t stream) {
+    if (n < 0 || !size_ok(size) || (n && (!me || !opp))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    init_kernel<<<persistent_grid(n, kThreads, kCtasPerSM), kThreads, 0, as_stream(stream)>>>(me, opp, player, n, size);
+    return launch_rc();
+}
+
+int bz_reversi_legal_mask(const uint64_t *me, const uint64_t *opp, uint64_t *mask, int64_t n, int size,
+                          bz_stream_t stream) {
+    if (n < 0 || !size_ok(size) || (n && (!me || !opp || !mask))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    const int grid = persistent_grid((n + 1) / 2, kThreads, kCtasPerSM);
+    if (aligned16(me) && aligned16(opp) && aligned16(mask))
+        legal_mask_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, mask, n, cell_mask(size));
+    else
+        legal_mask_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, mask, n, cell_mask(size));
+    return launch_rc();
+}
+
+int bz_reversi_apply(const uint64_t *me, const uint64_t *opp, const uint8_t *action, uint64_t *me_out,
+                     uint64_t *opp_out, uint8_t *err, int64_t n, int size, bz_stream_t stream) {
+    if (n < 0 || !size_ok(size) || (n && (!me || !opp || !action || !me_out || !opp_out))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    const int grid = persistent_grid((n + 1) / 2, kThreads, kCtasPerSM);
+    if (aligned16(me) && aligned16(opp) && aligned16(me_out) && aligned16(opp_out))
+        apply_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, action, me_out, opp_out, err, n, cell_mask(size));
+    else
+        apply_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, action, me_out, opp_out, err, n, cell_mask(size));
+    return launch_rc();
+}
+
+int bz_reversi_terminal(const uint64_t *me, const uint64_t *opp, uint8_t *over, int8_t *winner_for_me,
+                        uint8_t *cnt_me, uint8_t *cnt_opp, int64_t n, int size, bz_stream_t stream) {
+    if (n < 0 || !size_ok(size) || (n && (!me || !opp))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    const int grid = persistent_grid((n + 1) / 2, kThreads, kCtasPerSM);
+    if (aligned16(me) && aligned16(opp))
+        terminal_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, over, winner_for_me, cnt_me, cnt_opp, n, cell_mask(size));
+    else
+        terminal_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, over, winner_for_me, cnt_me, cnt_opp, n, cell_mask(size));
+    return launch_rc();
+}
+
+int bz_reversi_step_first_legal(const uint64_t *me, const uint64_t *opp, uint64_t *mask_out, uint8_t *action_out,
+                                uint64_t *me_out, uint64_t *opp_out, int64_t n, int size, bz_stream_t stream) {
+    if (n < 0 || !size_ok(size) || (n && (!me || !opp || !me_out || !opp_out))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    const int grid = persistent_grid((n + 1) / 2, kThreads, kCtasPerSM);
+    if (aligned16(me) && aligned16(opp) && aligned16(me_out) && aligned16(opp_out) && aligned16(mask_out))
+        step_first_legal_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, mask_out, action_out, me_out, opp_out, n, cell_mask(size));
+    else
+        step_first_legal_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(me, opp, mask_out, action_out, me_out, opp_out, n, cell_mask(size));
+    return launch_rc();
+}
+
+int bz_reversi_planes(const uint64_t *me, const uint64_t *opp, void *planes_bf16, int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!me || !opp || !planes_bf16))) return BZ_ERR_ARG;
+    if (!aligned16(planes_bf16)) return BZ_ERR_UNALIGNED;
+    if (n == 0) return BZ_OK;
+    planes_kernel<<<persistent_grid(n * 16, kThreads, kCtasPerSM), kThreads, 0, as_stream(stream)>>>(
+        me, opp, reinterpret_cast<uint4 *>(planes_bf16), n);
+    return launch_rc();
+}
+
+int bz_ttt_legal_mask(const uint16_t *x, const uint16_t *o, uint16_t *mask, int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!x || !o || !mask))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    ttt_mask_kernel<<<persistent_grid(n, kThreads, kCtasPerSM), kThreads, 0, as_stream(stream)>>>(x, o, mask, n);
+    return launch_rc();
+}
+
+int bz_ttt_apply(const uint16_t *x, const uint16_t *o, const uint8_t *action, const int8_t *player,
+                 uint16_t *x_out, uint16_t *o_out, uint8_t *err, int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!x || !o || !action || !player || !x_out || !o_out))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    ttt_apply_kernel<<<persistent_grid(n, kThreads, kCtasPerSM), kThreads, 0, as_stream(stream)>>>(x, o, action, player, x_out, o_out, err, n);
+    return launch_rc();
+}
+
+int bz_ttt_terminal(const uint16_t *x, const uint16_t *o, uint8_t *over, int8_t *winner, int64_t n,
+                    bz_stream_t stream) {
+    if (n < 0 || (n && (!x || !o))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    ttt_terminal_kernel<<<persistent_grid(n, kThreads, kCtasPerSM), kThreads, 0, as_stream(stream)>>>(x, o, over, winner, n);
+    return launch_rc();
+}
+
+int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int64_t *ops_per_thread,
+                        bz_stream_t stream) {
+    if (!sink || blocks <= 0 || threads <= 0 || threads > kThreads || iters <= 0) return BZ_ERR_ARG;
+    // per unrolled step: 8 x (SHF + LOP3); the xor/and (or xor/or) pair folds into one LOP3
+    if (ops_per_thread) *ops_per_thread = (int64_t)iters * 8 * 8 * 2;
+    int32_bench_kernel<<<blocks, threads, 0, as_stream(stream)>>>(sink, iters);
+    return launch_rc();
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+/*
+ * betazero_b200.h -- C ABI of the B200-native self-play engine for whaiproject/BetaZero.
+ *
+ * The reference is pure Python with no FFI layer; its drop-in boundary is the duck-typed board /
+ * player API.  This header is the boundary a native binding for that API
+ * would use: plain `extern "C"`, pointers + sizes, no torch / Python types.  Each entry point
+ * cites the reference code whose computation it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer (sm_100a, B200) unless a parameter says "host".
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *    stream), never allocates, never synchronises, never throws.  The caller owns all buffers.
+ *  - Return value: BZ_OK (0), BZ_ERR_ARG for a bad argument, or -(1000 + cudaError_t).
+ *  - Reversi boards are SoA uint64 pairs, MOVER-RELATIVE: `me` = discs of the side to move,
+ *    `opp` = the other side's.  bit = row*8 + col for every board size (4, 6, 8); cells
+ *    outside size x size are never set.  The reference's absolute view (`.board` with +1 = X,
+ *    -1 = O, reversi_board.py:7-11) is X = (player == +1 ? me : opp).
+ *  - Reversi action ids: a = row*8 + col, 64 = pass.  Policy vectors have BZ_REVERSI_ACTIONS
+ *    (65) entries.  Tic-tac-toe: a = row*3 + col, 9 entries.
+ *  - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef BETAZERO_B200_H
+#define BETAZERO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BZ_OK 0
+#define BZ_ERR_ARG (-1)
+#define BZ_ERR_UNALIGNED (-2)
+#define BZ_ABI_VERSION 1
+
+#define BZ_REVERSI_ACTIONS 65
+#define BZ_TTT_ACTIONS 9
+#define BZ_PASS 64
+
+#define BZ_GAME_REVERSI 0
+#define BZ_GAME_TTT 1
+
+typedef void *bz_stream_t; /* cudaStream_t */
+
+int bz_abi_version(void);
+/* static string for a return code of this library (host) */
+const char *bz_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Reversi environment (kernels K1..K3 of SURVEY.md section 2.1)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Start position for n boards: ReversiBoard.__init__, reversi_board.py:4-11, plus
+ * `current_player = 1` of ReversiTerminal.__init__, reversi_terminal.py:14.
+ * player may be NULL.  size in {4, 6, 8}. */
+int bz_reversi_init(uint64_t *me, uint64_t *opp, int8_t *player, int64_t n, int size, bz_stream_t stream);
+
+/* K1.  mask bit (r*8+c) == ReversiBoard.is_valid_move(r, c, mover) for all cells, i.e.
+ * generate_possible_moves(mover): reversi_board.py:25-41, 87-88.  24 B/board. */
+int bz_reversi_legal_mask(const uint64_t *me, const uint64_t *opp, uint64_t *mask, int64_t n, int size,
+                          bz_stream_t stream);
+
+/* K2.  ReversiBoard.make_move(r, c, mover), reversi_board.py:43-59, with the result expressed
+ * for the NEXT mover (me_out = old opp after flips, opp_out = old me + placed + flipped).
+ * action 64 = pass: board unchanged, sides swap (reversi_terminal.py:31-35).
+ * err[i] = 1 where the reference raises ValueError("Invalid move") (reversi_board.py:44-45), or
+ * for a pass while the mover has a move; the board is then copied through UNCHANGED and
+ * UNSWAPPED.  err may be NULL.  33 B/board (+1 with err). */
+int bz_reversi_apply(const uint64_t *me, const uint64_t *opp, const uint8_t *action, uint64_t *me_out,
+                     uint64_t *opp_out, uint8_t *err, int64_t n, int size, bz_stream_t stream);
+
+/* K3.  over = ReversiBoard.is_game_over() (reversi_board.py:61-65); winner_for_me / counts =
+ * get_score() (reversi_board.py:67-76) seen from the mover: +1 mover has more discs, -1 fewer,
+ * 0 tie.  Reported for every board (get_score does not require a finished game).  Any output
+ * pointer may be NULL.  20 B/board. */
+int bz_reversi_terminal(const uint64_t *me, const uint64_t *opp, uint8_t *over, int8_t *winner_for_me,
+                        uint8_t *cnt_me, uint8_t *cnt_opp, int64_t n, int size, bz_stream_t stream);
+
+/* K1+K2 fused: one ply of the reference episode loop (reversi_terminal.py:22-35) with the
+ * deterministic "first legal move" player: mask = legal moves; action = lowest set bit of mask,
+ * or 64 (pass) when mask == 0; boards advance to the next mover's view.  mask_out / action_out
+ * may be NULL.  41 B/board. */
+int bz_reversi_step_first_legal(const uint64_t *me, const uint64_t *opp, uint64_t *mask_out, uint8_t *action_out,
+                                uint64_t *me_out, uint64_t *opp_out, int64_t n, int size, bz_stream_t stream);
+
+/* K6 (stand-alone form).  Canonical network input, side to move = +1
+ * (players.py:85 `symbol * board`; generate_training_games.py:17-18): bf16 planes
+ * [n, 2, 8, 8], plane 0 = me, plane 1 = opp, 1.0 / 0.0.  16 B in + 256 B out per board. */
+int bz_reversi_planes(const uint64_t *me, const uint64_t *opp, void *planes_bf16, int64_t n, bz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tic-tac-toe environment (K4).  Absolute 9-bit boards x (+1) and o (-1), bit = row*3 + col.
+ * ---------------------------------------------------------------------------------------- */
+
+/* TicTacToeBoard.generate_possible_moves(), tic_tac_toe_board.py:42-43 (== is_valid_move :20-21) */
+int bz_ttt_legal_mask(const uint16_t *x, const uint16_t *o, uint16_t *mask, int64_t n, bz_stream_t stream);
+
+/* TicTacToeBoard.make_move(r, c, player), tic_tac_toe_board.py:23-29; err = ValueError. */
+int bz_ttt_apply(const uint16_t *x, const uint16_t *o, const uint8_t *action, const int8_t *player,
+                 uint16_t *x_out, uint16_t *o_out, uint8_t *err, int64_t n, bz_stream_t stream);
+
+/* TicTacToeBoard.is_game_over(), tic_tac_toe_board.py:31-40: lines of +1 are tested before
+ * lines of -1, then the full-board draw.  winner = +1 / -1 / 0, or 2 for Python's None. */
+int bz_ttt_terminal(const uint16_t *x, const uint16_t *o, uint8_t *over, int8_t *winner, int64_t n,
+                    bz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched MCTS (K5..K8).  The reference has no MCTS; the semantics are those frozen in
+ * oracle/mcts_ref.py, and the entry point this serves is Player.get_move(board) -> (row, col)
+ * (reversi_players.py:5-8, players.py:6-9).
+ *
+ * One warp owns one tree.  All pools are caller-allocated SoA arrays resident in HBM.
+ * Tree-local indices are int32; a tree's slice of a per-edge array starts at
+ * (int64)tree * edge_cap.
+ * ---------------------------------------------------------------------------------------- */
+
+/* edge_meta layout: bits 0..6 action, bits 7..12 number of edges of the child node (0 = child
+ * not a normal node), bits 13..31 child's first edge (tree-local).  With child_n == 0 the
+ * offset field holds BZ_META_UNEXPANDED or BZ_META_TERMINAL + {0,1,2} for a terminal child
+ * worth {-1, 0, +1} to ITS side to move. */
+#define BZ_META_OFF_SHIFT 13
+#define BZ_META_N_SHIFT 7
+#define BZ_META_UNEXPANDED 0x7FFFFu
+#define BZ_META_TERMINAL 0x7FFF0u
+#define BZ_MAX_EDGE_CAP 0x7FFF0
+
+/* leaf_status values */
+#define BZ_LEAF_EVAL 0     /* needs the evaluator's (prior weights, value) */
+#define BZ_LEAF_TERMINAL 1 /* game over at the leaf: value known, evaluator output ignored */
+#define BZ_LEAF_ERROR 2    /* pool overflow; tree flagged in `error`, iteration skipped */
+
+typedef struct bz_tree_pools {
+    int32_t game;       /* BZ_GAME_REVERSI / BZ_GAME_TTT */
+    int32_t board_size; /* Reversi: 4, 6, 8 */
+    int32_t n_trees;
+    int32_t n_actions; /* 65 / 9: row stride of prior_w, visit_counts, pi */
+    int32_t edge_cap;  /* edges per tree (<= BZ_MAX_EDGE_CAP); worst case 33 per expanded node */
+    int32_t max_depth; /* path capacity per tree */
+    float c_puct;
+    int32_t reserved;
+    /* per tree [n_trees] */
+    uint64_t *root_me, *root_opp;
+    uint32_t *root_meta;  /* like edge_meta, for the (virtual) edge into the root */
+    int32_t *edge_count;  /* bump allocator */
+    int32_t *sim_count;   /* completed select/expand iterations since reset */
+    int32_t *depth_sum;   /* sum of path lengths of those iterations (mean depth d of the roofline model) */
+    int32_t *error;       /* sticky: 1 = edge pool overflow, 2 = path overflow */
+    /* per edge [n_trees * edge_cap] */
+    int32_t *edge_N;
+    float *edge_W;
+    float *edge_P;
+    uint32_t *edge_meta;
+    uint64_t *edge_me, *edge_opp; /* board AFTER the edge, for the child's mover (set on expansion) */
+    /* pending leaf, per tree */
+    int32_t *path;      /* [n_trees * max_depth] tree-local edge indices, root first */
+    int32_t *path_len;  /* [n_trees] */
+    uint64_t *leaf_me, *leaf_opp;
+    uint64_t *leaf_mask; /* legal cells of the leaf's mover (0 with status EVAL = the mover must pass) */
+    uint8_t *leaf_status;
+    float *leaf_value;  /* terminal value for the leaf's mover */
+    void *leaf_planes;  /* bf16 [n_trees, 2, 8, 8] canonical planes of the leaf (K6) */
+} bz_tree_pools;
+
+/* Empty every tree and set its root position (mover-relative). */
+int bz_mcts_reset(const bz_tree_pools *pools, const uint64_t *root_me, const uint64_t *root_opp,
+                  bz_stream_t stream);
+
+/* K5 (+K6 fused): one PUCT descent per tree.  Writes path/path_len, the leaf board, its status
+ * and its canonical bf16 planes. */
+int bz_mcts_select(const bz_tree_pools *pools, bz_stream_t stream);
+
+/* K6 on its own: re-pack leaf_me/leaf_opp into leaf_planes (select already does this). */
+int bz_mcts_gather(const bz_tree_pools *pools, bz_stream_t stream);
+
+/* K7: expand the pending leaf with priors = prior_w renormalised over its legal actions
+ * (prior_w: float32 [n_trees, n_actions], >= 0; if the legal weights sum to 0 the prior is
+ * uniform) and back `value` (float32 [n_trees], for the leaf's mover) up the path.  Terminal
+ * leaves back up their exact game result instead. */
+int bz_mcts_expand_backup(const bz_tree_pools *pools, const float *prior_w, const float *value,
+                          bz_stream_t stream);
+
+/* K7+K5+K6 in one launch: finish iteration i with the evaluator's output, start iteration i+1. */
+int bz_mcts_step(const bz_tree_pools *pools, const float *prior_w, const float *value, bz_stream_t stream);
+
+/* K8: root visit counts (int32 [n_trees, n_actions]), pi = N / sum N and q = W / N (float32,
+ * same shape; either may be NULL), scattered by action, zeros elsewhere. */
+int bz_mcts_root_policy(const bz_tree_pools *pools, int32_t *visit_counts, float *pi, float *q,
+                        bz_stream_t stream);
+
+/* Most-visited action per tree, lowest action id on ties (the argmax-over-legal pick of
+ * players.py:92-98 applied to visit counts); 255 if the root has no visits. */
+int bz_mcts_best_action(const bz_tree_pools *pools, uint8_t *action, bz_stream_t stream);
+
+/* Parity-mode evaluator: deterministic integer-hash "pseudo-net" on (me, opp); weights 1..32
+ * and value k/8 are exact in fp32, identical to oracle/mcts_ref.py:hash_eval. */
+int bz_hash_eval(const uint64_t *me, const uint64_t *opp, uint64_t salt, int n_actions, float *prior_w,
+                 float *value, int64_t n, bz_stream_t stream);
+
+/* INT32 issue-rate microbenchmark (LOP3 / SHF / IADD3 mix) for the env roofline denominator:
+ * every thread runs `iters` rounds of 64 dependent-chain-free integer instructions x 4 chains.
+ * sink: device uint32 [1].  Returns the number of integer instructions per thread in *ops_per_thread
+ * (host pointer). */
+int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int64_t *ops_per_thread,
+                        bz_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BETAZERO_B200_H */

@@ -1,0 +1,221 @@
+"""GPU parity: batched MCTS kernels (K5-K8) through the C ABI vs the sequential oracle.
+
+Visit counts must be BIT-EXACT (deterministic tie-breaking, Dirichlet noise off); W / P are
+compared exactly too (they are, by construction of the fp32 op order), and Q / pi within the
+north-star's 1e-5 relative tolerance.  MCTS parity is unpinned by the reference (it has no MCTS):
+the oracle is oracle/mcts_ref.py (golden) and its C restatement (oracle.c)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: Q values and policy targets within 1e-5 relative
+
+
+def _search(me_h, opp_h, n_sims, salt, game=0, size=8, c_puct=1.25, **kw):
+    from betazero_b200 import env, mcts
+
+    pools = mcts.TreePools(len(me_h), n_sims, game=game, board_size=size, c_puct=c_puct)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(salt), **kw)
+    cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
+    return s, cnt.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy()
+
+
+def _root_W_P(s):
+    """pull root-edge W and P back, scattered by action"""
+    p = s.pools
+    B, A = p.n_trees, p.n_actions
+    meta = p.root_meta.cpu().numpy().view(np.uint32)
+    W = np.zeros((B, A), np.float32)
+    P = np.zeros((B, A), np.float32)
+    eW, eP, eM = p.edge_W.cpu().numpy(), p.edge_P.cpu().numpy(), p.edge_meta.cpu().numpy().view(np.uint32)
+    for t in range(B):
+        n, off = (meta[t] >> 7) & 63, meta[t] >> 13
+        for i in range(n):
+            e = t * p.edge_cap + off + i
+            W[t, eM[e] & 127] = eW[e]
+            P[t, eM[e] & 127] = eP[e]
+    return W, P
+
+
+@pytest.mark.parametrize("prefix", ["rev8_playout_s48", "rev8_start_s400", "rev8_pass_s64"])
+def test_reversi_matches_golden(golden_mcts, prefix):
+    g = golden_mcts
+    n_sims, salt = (int(v) for v in g[prefix + "_meta"])
+    s, cnt, pi, q = _search(g[prefix + "_me"], g[prefix + "_opp"], n_sims, salt, c_puct=float(g["c_puct"]))
+    assert np.array_equal(cnt, g[prefix + "_counts"])
+    W, P = _root_W_P(s)
+    assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])
+    gc = g[prefix + "_counts"].astype(np.float32)
+    exp_pi = gc / gc.sum(1, keepdims=True)
+    exp_q = np.where(gc > 0, g[prefix + "_W"] / np.maximum(gc, 1), 0)
+    np.testing.assert_allclose(pi, exp_pi, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(q, exp_q, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("n_sims", [25, 100])
+def test_config1_ttt_selfplay_visit_counts(golden_mcts, n_sims):
+    """BASELINE config 1: tic-tac-toe MCTS self-play, root visit counts of every ply bit-exact"""
+    from betazero_b200 import mcts
+
+    g = golden_mcts
+    for salt in range(4):
+        p = f"ttt_game_s{n_sims}_k{salt}"
+        s, cnt, pi, q = _search(g[p + "_me"], g[p + "_opp"], n_sims, salt, game=mcts.GAME_TTT, c_puct=float(g["c_puct"]))
+        assert np.array_equal(cnt, g[p + "_counts"])
+        assert np.array_equal(s.best_action().cpu().numpy(), g[p + "_action"])
+
+
+@pytest.mark.parametrize("size,n_sims", [(4, 40), (6, 24)])
+def test_small_boards_match_golden(golden_mcts, size, n_sims):
+    g = golden_mcts
+    p = f"rev{size}_game_s{n_sims}"
+    s, cnt, _, _ = _search(g[p + "_me"], g[p + "_opp"], n_sims, 2, size=size, c_puct=float(g["c_puct"]))
+    assert np.array_equal(cnt, g[p + "_counts"])
+    assert np.array_equal(s.best_action().cpu().numpy(), g[p + "_action"])
+
+
+def test_config3_1024_trees_100_sims_vs_c_oracle():
+    """BASELINE config 3 shape: 1024 concurrent trees, 100 sims/move (hash evaluator for parity)."""
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(1024, seed=5)
+    s, cnt, pi, q = _search(me_h, opp_h, 100, salt=17)
+    r_cnt, r_W, r_P, ctr = po.search_hash(me_h, opp_h, 100, po.GAME_REVERSI, 8, 1.25, 17)
+    assert np.array_equal(cnt, r_cnt)
+    W, P = _root_W_P(s)
+    assert np.array_equal(W, r_W) and np.array_equal(P, r_P)
+    st = s.stats()
+    assert st["sims"] == ctr["sims"] == 1024 * 100
+    assert abs(st["mean_depth"] - ctr["sum_depth"] / ctr["sims"]) < 1e-9
+    assert st["edges"] == ctr["edges"]
+
+
+def test_800_sims_vs_c_oracle():
+    """the headline search length (800 sims/move) on 128 trees, graph + fused path"""
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(128, seed=6)
+    s, cnt, _, _ = _search(me_h, opp_h, 800, salt=1)
+    r_cnt, _, _, _ = po.search_hash(me_h, opp_h, 800, po.GAME_REVERSI, 8, 1.25, 1)
+    assert np.array_equal(cnt, r_cnt)
+
+
+def test_fused_graph_and_plain_paths_agree():
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(300, seed=8)
+    ref = None
+    for kw in (dict(use_graph=False, fused=False), dict(use_graph=False, fused=True),
+               dict(use_graph=True, fused=True, graph_unroll=8), dict(use_graph=True, fused=False, graph_unroll=5)):
+        _, cnt, pi, q = _search(me_h, opp_h, 70, salt=3, **kw)
+        if ref is None:
+            ref = (cnt, pi, q)
+        else:
+            assert np.array_equal(cnt, ref[0]) and np.array_equal(pi, ref[1]) and np.array_equal(q, ref[2])
+
+
+def test_lockstep_float_priors_vs_c_oracle():
+    """real-net-like float priors and values: feed the SAME (w, v) to the GPU trees and to the
+    oracle trees at every iteration and compare leaves, statuses and final statistics bit for bit"""
+    from betazero_b200 import env, mcts
+    from oracle import pyoracle as po
+
+    B, n_sims = 96, 150
+    me_h, opp_h = po.playout_boards(B, seed=12)
+    pools = mcts.TreePools(B, n_sims, c_puct=2.0)
+    s = mcts.BatchedMCTS(pools, None, use_graph=False)
+    s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
+    trees = [po.OracleTree(po.GAME_REVERSI, 8, 2.0) for _ in range(B)]
+    for t, m, o in zip(trees, me_h, opp_h):
+        t.reset_wire(m, o)
+    rng = np.random.default_rng(0)
+    s.select()
+    for it in range(n_sims):
+        lm, lo = env.to_host_u64(pools.leaf_me), env.to_host_u64(pools.leaf_opp)
+        st = pools.leaf_status.cpu().numpy()
+        plen = pools.path_len.cpu().numpy()
+        w = (rng.random((B, 65)) ** 4).astype(np.float32)
+        w[rng.random((B, 65)) < 0.1] = 0.0  # exact zeros happen with bf16 softmax
+        v = rng.uniform(-1, 1, B).astype(np.float32)
+        for i, t in enumerate(trees):
+            ost, ome, oopp, od = t.select()
+            assert (ost, ome, oopp, od) == (int(st[i]), int(lm[i]), int(lo[i]), int(plen[i])), (it, i)
+            t.expand_backup(w[i], v[i])
+        s.prior_w.copy_(torch.from_numpy(w))
+        s.value.copy_(torch.from_numpy(v))
+        if it + 1 < n_sims:
+            s.step()
+        else:
+            s.expand_backup()
+    cnt, pi, q = (x.cpu().numpy() for x in s.root_policy())
+    W, P = _root_W_P(s)
+    for i, t in enumerate(trees):
+        c, w_, p_ = t.root_stats()
+        assert np.array_equal(cnt[i], c) and np.array_equal(W[i], w_) and np.array_equal(P[i], p_)
+    s.check_errors()
+
+
+def test_leaf_planes_are_canonical_leaf_boards():
+    from betazero_b200 import env, mcts
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(257, seed=2)
+    pools = mcts.TreePools(257, 40)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(4), use_graph=False)
+    s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
+    s.run(39)
+    s.select()
+    exp = env.planes(pools.leaf_me, pools.leaf_opp)
+    assert torch.equal(pools.leaf_planes, exp)
+    pools.leaf_planes.zero_()
+    from betazero_b200 import _lib
+    _lib.check(_lib.load().bz_mcts_gather(pools._ref, _lib.stream_ptr()))
+    assert torch.equal(pools.leaf_planes, exp)
+
+
+def test_terminal_and_pass_roots():
+    from betazero_b200 import env, mcts
+
+    # tree 0: full board (game over).  tree 1: mover owns b1, opponent a1, rest empty: the mover
+    # cannot outflank a corner disc, but the opponent can play c1 -> the mover must pass.
+    me_h = np.array([(1 << 64) - 1 - 0xFF, 0x2], np.uint64)
+    opp_h = np.array([0xFF, 0x1], np.uint64)
+    pools = mcts.TreePools(2, 16)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(0), use_graph=False)
+    cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 16)
+    cnt = cnt.cpu().numpy()
+    assert cnt[0].sum() == 0  # finished game: nothing to search
+    best = s.best_action().cpu().numpy()
+    assert best[0] == 255
+    assert cnt[1, 64] == 15 and cnt[1, :64].sum() == 0 and best[1] == 64
+    assert pi.cpu().numpy()[1, 64] == 1.0
+
+
+def test_edge_pool_overflow_is_detected():
+    from betazero_b200 import _lib, env, mcts
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(8, seed=1)
+    pools = mcts.TreePools(8, 64, edge_cap=40)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(0), use_graph=False)
+    with pytest.raises(_lib.BzError, match="overflow"):
+        s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 64)
+
+
+def test_hash_eval_kernel_matches_oracle():
+    from betazero_b200 import _lib, env
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.synthetic_boards(500, seed=21)
+    for A in (9, 65):
+        w = torch.empty((500, A), dtype=torch.float32, device="cuda")
+        v = torch.empty(500, dtype=torch.float32, device="cuda")
+        _lib.check(_lib.load().bz_hash_eval(_lib.dptr(env.to_device_u64(me_h)), _lib.dptr(env.to_device_u64(opp_h)), 77, A,
+                                            _lib.dptr(w), _lib.dptr(v), 500, _lib.stream_ptr()))
+        w, v = w.cpu().numpy(), v.cpu().numpy()
+        for i in range(0, 500, 7):
+            rw, rv = po.hash_eval(me_h[i], opp_h[i], 77, A)
+            assert np.array_equal(w[i], rw) and v[i] == rv

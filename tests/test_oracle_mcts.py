@@ -1,0 +1,128 @@
+"""CPU tests: the MCTS oracles.  The reference has no MCTS, so these pin (a) the C restatement
+(oracle.c part 2) against the Python definition (oracle/mcts_ref.py), and (b) both against the
+golden visit counts that mcts_ref.py produced when driving the LIVE reference board classes
+(tests/golden/mcts.npz, oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import mcts_ref as mr
+from oracle import pyoracle as po
+from oracle import ref_shim
+
+
+def _c_search(me, opp, n_sims, salt, game, size, c_puct):
+    return po.search_hash(np.array([me], np.uint64), np.array([opp], np.uint64), n_sims, game, size, c_puct, salt)
+
+
+@pytest.mark.parametrize("prefix", ["rev8_playout_s48", "rev8_start_s400", "rev8_pass_s64"])
+def test_c_mcts_matches_golden_reversi(golden_mcts, prefix):
+    g = golden_mcts
+    n_sims, salt = (int(v) for v in g[prefix + "_meta"])
+    cnt, W, P, _ = po.search_hash(g[prefix + "_me"], g[prefix + "_opp"], n_sims, po.GAME_REVERSI, 8,
+                                  float(g["c_puct"]), salt)
+    assert np.array_equal(cnt, g[prefix + "_counts"])
+    assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])
+    if prefix == "rev8_pass_s64":  # the only root action is pass, visited n_sims - 1 times
+        assert (cnt[:, 64] == n_sims - 1).all() and (cnt[:, :64] == 0).all()
+
+
+@pytest.mark.parametrize("n_sims", [25, 100])
+def test_c_mcts_matches_golden_ttt_selfplay(golden_mcts, n_sims):
+    """BASELINE config 1: tic-tac-toe MCTS self-play, root visit counts at every ply."""
+    g = golden_mcts
+    for salt in range(4):
+        p = f"ttt_game_s{n_sims}_k{salt}"
+        cnt, _, _, _ = po.search_hash(g[p + "_me"], g[p + "_opp"], n_sims, po.GAME_TTT, 3, float(g["c_puct"]), salt)
+        assert np.array_equal(cnt, g[p + "_counts"])
+        assert np.array_equal(cnt.argmax(1), g[p + "_action"])
+
+
+@pytest.mark.parametrize("size,n_sims", [(4, 40), (6, 24)])
+def test_c_mcts_matches_golden_small_boards(golden_mcts, size, n_sims):
+    g = golden_mcts
+    p = f"rev{size}_game_s{n_sims}"
+    cnt, _, _, _ = po.search_hash(g[p + "_me"], g[p + "_opp"], n_sims, po.GAME_REVERSI, size, float(g["c_puct"]), 2)
+    assert np.array_equal(cnt, g[p + "_counts"])
+
+
+def test_python_definition_on_oracle_boards_matches_golden(golden_mcts):
+    """mcts_ref.py driving the C-restated board classes reproduces what it produced on the live
+    reference classes: the board restatement is interchangeable inside the search."""
+    g = golden_mcts
+    game = mr.ReversiGame(po.OracleReversiBoard, 8)
+    n_sims, salt = (int(v) for v in g["rev8_playout_s48_meta"])
+    for k in (0, 7, 23, 40, 58):
+        me, opp = int(g["rev8_playout_s48_me"][k]), int(g["rev8_playout_s48_opp"][k])
+        b = po.OracleReversiBoard(size=8)
+        b.board = po.wire_to_grid(me, opp, 8)
+        m = mr.MCTS(game, float(g["c_puct"]), lambda a, c: mr.hash_eval(a, c, salt, 65))
+        m.reset(b, 1)
+        m.run(n_sims)
+        cnt, W, P = m.root_stats()
+        assert np.array_equal(cnt, g["rev8_playout_s48_counts"][k])
+        assert np.array_equal(W, g["rev8_playout_s48_W"][k]) and np.array_equal(P, g["rev8_playout_s48_P"][k])
+
+
+def test_stepwise_c_tree_equals_python_definition_with_float_priors():
+    """non-integer priors/values (like a real net's): C and Python must still agree bit for bit"""
+    rng = np.random.default_rng(11)
+    game = mr.ReversiGame(po.OracleReversiBoard, 8)
+    table = {}
+
+    def ev(me, opp):
+        if (me, opp) not in table:
+            w = rng.random(65).astype(np.float32) ** 3
+            table[(me, opp)] = (w, np.float32(rng.uniform(-1, 1)))
+        return table[(me, opp)]
+
+    b, p = game.initial()
+    m = mr.MCTS(game, 1.7, ev)
+    m.reset(b, p)
+    t = po.OracleTree(po.GAME_REVERSI, 8, 1.7)
+    t.reset(np.asarray(b.board), p)
+    for _ in range(300):
+        st, me, opp = m.select()
+        st2, me2, opp2, _ = t.select()
+        assert (st, me, opp) == (st2, me2, opp2)
+        w, v = ev(me, opp) if st == 0 else (None, 0.0)
+        m.expand_backup(w, v)
+        t.expand_backup(w, v)
+    for a, b_ in zip(m.root_stats(), t.root_stats()):
+        assert np.array_equal(a, b_)
+    assert t.counters()["sum_depth"] == m.sum_depth
+
+
+def test_hash_eval_c_equals_python():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        me, opp, salt = (int(v) for v in rng.integers(0, 2 ** 63, size=3))
+        for A in (9, 65):
+            w1, v1 = mr.hash_eval(me, opp, salt, A)
+            w2, v2 = po.hash_eval(me, opp, salt, A)
+            assert np.array_equal(w1, w2) and v1 == v2
+            assert w1.min() >= 1 and w1.max() <= 32 and -1 <= v1 <= 0.875
+
+
+def test_zero_weight_priors_fall_back_to_uniform():
+    t = po.OracleTree(po.GAME_TTT, 3, 1.0)
+    t.reset(np.zeros(9, np.int8), 1)
+    t.select()
+    t.expand_backup(np.zeros(9, np.float32), 0.0)
+    _, _, P = t.root_stats()
+    assert np.array_equal(P, np.full(9, np.float32(1) / np.float32(9), np.float32))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="live reference not present")
+def test_definition_on_live_reference_matches_c(golden_mcts):
+    RB = ref_shim.reversi_board_cls()
+    game = mr.ReversiGame(RB, 8)
+    b, p = game.initial()
+    for (r, c) in ((2, 4), (2, 3)):
+        b, p = game.next(b, p, r * 8 + c)
+    m = mr.MCTS(game, 1.25, lambda a, c: mr.hash_eval(a, c, 9, 65))
+    m.reset(b, p)
+    m.run(120)
+    me, opp = game.wire(b, p)
+    cnt, W, P, _ = _c_search(me, opp, 120, 9, po.GAME_REVERSI, 8, 1.25)
+    c0, w0, p0 = m.root_stats()
+    assert np.array_equal(cnt[0], c0) and np.array_equal(W[0], w0) and np.array_equal(P[0], p0)
