@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- Reversi 8x8 self-play MCTS throughput on B200 (BASELINE.json's headline metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --steps K --warmup W     # the CPU arm (oracle port) on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU (games shard, no collective)
+
+A "step" is one lockstep ply of self-play for every game of the rank: one batched MCTS of
+``--sims`` iterations over ``--games`` concurrent trees (select -> gather -> net -> expand/backup,
+every iteration) followed by the move/terminal/replay kernel.  Workload at N=1: BASELINE config
+"Reversi 8x8 self-play, 800 sims/move, 4096 games per GPU".  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reversi8x8_selfplay_mcts_sims_per_sec"
+UNIT = "sims/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games (trees) per GPU")
+    ap.add_argument("--sims", type=int, default=800, help="MCTS iterations per move")
+    ap.add_argument("--net", default="mlp", choices=["mlp", "resnet"])
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--graph-unroll", type=int, default=16)
+    ap.add_argument("--cpu-trees", type=int, default=256, help="trees of the CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the env-kernel / INT32 side measurements")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_selfplay_sample(n_trees: int, n_sims: int, net_kind: str, hidden: int, budget_s: float, steps: int | None,
+                        warmup: int = 1):
+    """The oracle port on the host cores: C sequential MCTS trees (oracle.c, OpenMP over trees)
+    stepped in lockstep with the SAME policy/value net evaluated by PyTorch on the CPU in fp32.
+    One step = one n_sims-iteration search from each of n_trees reachable roots."""
+    import numpy as np
+    import torch
+
+    from betazero_b200 import net as netmod
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = netmod.make_net(net_kind, hidden=hidden, seed=0, device="cpu", dtype=torch.float32)
+    me, opp = po.playout_boards(n_trees, seed=42)
+    forest = po.OracleForest(n_trees)
+
+    def one_step():
+        forest.reset(me, opp)
+        with torch.no_grad():
+            for _ in range(n_sims):
+                forest.select()
+                logits, v = net(torch.from_numpy(forest.planes))
+                w = torch.softmax(logits, dim=-1).numpy()
+                forest.expand_backup(w, v.numpy())
+
+    t0 = time.perf_counter()
+    one_step()  # warm-up, also calibrates the step count to the budget
+    t_one = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        one_step()
+    if steps is None:
+        steps = max(1, min(50, int(budget_s / max(t_one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    sims = steps * n_trees * n_sims
+    return {"value": sims / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {n_trees} trees x {n_sims} sims (C oracle trees, OpenMP {po.num_threads()} threads, "
+                      f"torch fp32 {net_kind} net on CPU, batch {n_trees}); {dt:.1f} s",
+            "positions_per_sec": steps * n_trees / dt, "ms_per_step": 1e3 * dt / steps, "steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    # W warm-up steps, then exactly K timed steps; one step = one search over the bounded sample
+    r2 = cpu_selfplay_sample(args.cpu_trees, args.sims, args.net, args.hidden, 0, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r2["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r2["steps"], "warmup": args.warmup, "ms_per_step": r2["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {k: r2[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r2["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "positions_per_sec": r2["positions_per_sec"], "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
+            "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
+            "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
+            "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from betazero_b200 import env, mcts, selfplay
+    from betazero_b200 import net as netmod
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, S = args.games, args.sims
+    net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
+    sp = selfplay.BatchedSelfPlay(B, S, mcts.NetEvaluator(net), temp_plies=8, seed=1234, rank=rank, world=world,
+                                  graph_unroll=args.graph_unroll)
+    sp.prepare()
+    for _ in range(args.warmup):
+        sp.play_move()
+    barrier()
+
+    # ---- timed region 1: device-resident self-play (value) ------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sp.total_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sp.play_move()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sp.total_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    sp.mcts.check_errors()
+    tstats = sp.mcts.stats()  # d and b of the last search
+
+    # ---- timed region 2: end to end through the host-facing search API (e2e) ---------------------
+    # per step: roots in pinned host memory -> H2D -> n_sims-iteration search -> pi + move -> D2H
+    h_me = sp.me.cpu().pin_memory()
+    h_opp = sp.opp.cpu().pin_memory()
+    d_me, d_opp = torch.empty_like(sp.me), torch.empty_like(sp.opp)
+    h_pi = torch.empty((B, 65), dtype=torch.float32).pin_memory()
+    h_act = torch.empty(B, dtype=torch.uint8).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        d_me.copy_(h_me, non_blocking=True)
+        d_opp.copy_(h_opp, non_blocking=True)
+        sp.mcts.reset(d_me, d_opp)
+        sp.mcts.run(S)
+        _, pi, _ = sp.mcts.root_policy()
+        act = sp.mcts.best_action()
+        h_pi.copy_(pi, non_blocking=True)
+        h_act.copy_(act, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    h2d = 2 * B * 8
+    d2h = B * 65 * 4 + B
+
+    # ---- the dominant kernel (fused expand/backup + select + gather), timed launch by launch ------
+    sp.mcts.reset(sp.me, sp.opp)
+    sp.mcts.select()
+    evs = []
+    n_probe = min(S - 1, 400)
+    for i in range(n_probe):
+        sp.mcts.evaluate()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sp.mcts.step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = [a.elapsed_time(b) for a, b in evs]
+    step_kernel_ms = sum(k_ms[len(k_ms) // 2:]) / max(1, len(k_ms) - len(k_ms) // 2)  # deep-tree half
+
+    # max over ranks, whole-job aggregate
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0].item()), float(t[1].item())
+    total_sims = world * args.steps * B * S
+    value = total_sims / (ms * 1e-3)
+    e2e_value = total_sims / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        d = tstats["mean_depth"]
+        bmean = tstats["edges"] / max(1, tstats["sims"])  # edges created per iteration ~ mean children of a new node
+        bytes_per_sim = 28 * d + 12 * d * bmean + 13 * bmean + 312
+        achieved = bytes_per_sim * B / (step_kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("mcts_step_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 tree statistics / u64 bitboards / bf16 net", "data": "synthetic",
+            "config": workload_config(args),
+            "positions_per_sec": world * args.steps * B / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "step_kernel<reversi> (K7 expand/backup + K5 select + K6 gather)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel_ms": step_kernel_ms,
+                         "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
+                         "sims_per_launch": B},
+            "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
+            "selfplay": sp.stats(),
+        }
+        if not args.no_extra and world == 1:
+            line["extra"] = side_measurements(torch, env, peak)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = {k: v for k, v in cpu_selfplay_sample(
+                args.cpu_trees, S, args.net, args.hidden, args.cpu_seconds, None).items()
+                if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_measurements(torch, env, hbm_peak):
+    """Config-2 env kernels at 2^26 boards (working set > L2) and the INT32 issue-rate microbench."""
+    out = {}
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randint(-(2 ** 63), 2 ** 63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.randint(-(2 ** 63), 2 ** 63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    c = torch.randint(-(2 ** 63), 2 ** 63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    me, opp = a & b, ~a & c
+    del a, b, c
+    mask = torch.empty_like(me)
+    outs = (torch.empty_like(me), torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty_like(me), torch.empty_like(me))
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t1 = timed(lambda: env.legal_mask(me, opp, out=mask))
+    t2 = timed(lambda: env.step_first_legal(me, opp, out=outs))
+    out["env_legal_mask"] = {"boards": n, "ms": t1, "boards_per_sec": n / t1 * 1e3, "GBps": 24 * n / t1 / 1e6,
+                             "hbm_frac": 24 * n / t1 / 1e6 / hbm_peak}
+    out["env_step_first_legal"] = {"boards": n, "ms": t2, "boards_per_sec": n / t2 * 1e3, "GBps": 41 * n / t2 / 1e6,
+                                   "hbm_frac": 41 * n / t2 / 1e6 / hbm_peak}
+    blocks, threads, iters = 148 * 8, 256, 2048
+    ops = env.int32_microbench(blocks, threads, iters)
+    t3 = timed(lambda: env.int32_microbench(blocks, threads, iters), reps=3)
+    out["int32_peak"] = {"lane_ops_per_sec": ops / t3 * 1e3, "ms": t3,
+                         "note": "SHF+LOP3 mix, 8 independent chains/thread, 148x8 CTAs x 256 threads"}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

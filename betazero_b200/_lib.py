@@ -30,10 +30,24 @@ class BzTreePools(C.Structure):
     ]
 
 
+class BzSelfplayState(C.Structure):
+    """Mirror of ``bz_selfplay_state`` (include/betazero_b200.h)."""
+
+    _fields_ = [
+        ("n_games", C.c_int32), ("board_size", C.c_int32), ("max_plies", C.c_int32), ("temp_plies", C.c_int32),
+        ("seed", C.c_uint64), ("id_stride", C.c_int64), ("replay_cap", C.c_int64),
+        ("me", ptr), ("opp", ptr), ("player", ptr), ("ply", ptr), ("game_id", ptr),
+        ("hist_me", ptr), ("hist_opp", ptr), ("hist_player", ptr), ("hist_action", ptr), ("hist_pi", ptr),
+        ("rp_me", ptr), ("rp_opp", ptr), ("rp_pi", ptr), ("rp_z", ptr), ("rp_game", ptr), ("rp_ply", ptr),
+        ("counters", ptr),
+    ]
+
+
 # name -> argtypes; every function returns int.  Must list EVERY symbol of include/betazero_b200.h
 # (tests/test_abi.py cross-checks this table against the header).
 _I64, _INT, _U64, _F = C.c_int64, C.c_int, C.c_uint64, C.c_float
 _PP = C.POINTER(BzTreePools)
+_SP = C.POINTER(BzSelfplayState)
 SIGNATURES = {
     "bz_abi_version": [],
     "bz_error_string": [_INT],
@@ -54,6 +68,9 @@ SIGNATURES = {
     "bz_mcts_root_policy": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_best_action": [_PP, ptr, ptr],
     "bz_hash_eval": [ptr, ptr, _U64, _INT, ptr, ptr, _I64, ptr],
+    "bz_selfplay_init": [_SP, _I64, ptr],
+    "bz_selfplay_advance": [_SP, _PP, ptr, ptr],
+    "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],
 }
 

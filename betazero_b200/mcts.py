@@ -55,8 +55,9 @@ class TreePools:
             return torch.empty(max(n, 1), dtype=dt, device=dev)
 
         self.root_me, self.root_opp = e(B, torch.int64), e(B, torch.int64)
-        self.root_meta = e(B, torch.int32)
-        self.edge_count, self.sim_count = e(B, torch.int32), e(B, torch.int32)
+        # valid "empty tree" state from the start, so no kernel ever walks uninitialised memory
+        self.root_meta = torch.full((max(B, 1),), -8192, dtype=torch.int32, device=dev)  # meta(UNEXPANDED)
+        self.edge_count, self.sim_count = torch.zeros(max(B, 1), dtype=torch.int32, device=dev), e(B, torch.int32)
         self.depth_sum, self.error = e(B, torch.int32), torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
         self.edge_N, self.edge_W, self.edge_P = e(E, torch.int32), e(E, torch.float32), e(E, torch.float32)
         self.edge_meta = e(E, torch.int32)
@@ -165,8 +166,18 @@ class BatchedMCTS:
     # -- the search ----------------------------------------------------------------------------
     def _capture(self) -> None:
         # warm up on a side stream (cuBLAS workspaces, lazy module init), then capture `unroll`
-        # [evaluate -> step] blocks.  Replaying on a fresh pending leaf is harmless: warm-up runs
-        # happen before reset() of the real search.
+        # [evaluate -> step] blocks.  The warm-up really runs, so the pools must hold valid trees:
+        # reset them to start positions first (the caller resets again for the real search).
+        p = self.pools
+        if p.game == GAME_TTT:
+            rm = torch.zeros(p.n_trees, dtype=torch.int64, device=p.device)
+            ro = torch.zeros_like(rm)
+        else:
+            from . import env
+
+            rm, ro, _ = env.reversi_init(p.n_trees, p.board_size, device=p.device)
+        self.reset(rm, ro)
+        self.select()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -1,0 +1,101 @@
+"""Policy/value networks (plain PyTorch -- the net is the only dense contraction on the path and
+the only user of the tensor cores; it is library code, not the product).
+
+``PolicyValueMLP`` is the reference's only architecture -- ``TicTacToeNet``, a 4-layer ReLU MLP
+``in -> H -> H -> H -> actions`` (src/tic_tac_toe/SL/neural_networks.py:4-30, hidden 256 in
+src/tic_tac_toe/SL/train.py:186) -- widened to the 8x8 board and given the value head AlphaZero
+needs.  ``PolicyValueResNet`` is the usual AlphaZero tower for stronger play.
+
+Every net maps the bf16 canonical planes written by the leaf-gather kernel to
+``(policy logits [B, A], value [B] in [-1, 1])``.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+N_ACTIONS = 65
+TTT_ACTIONS = 9
+
+
+class PolicyValueMLP(nn.Module):
+    """in -> H -> H -> H -> (A logits, 1 value): TicTacToeNet (neural_networks.py:4-30) + value head."""
+
+    def __init__(self, in_features: int = 128, hidden: int = 256, n_actions: int = N_ACTIONS):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden)
+        self.fc2 = nn.Linear(hidden, hidden)
+        self.fc3 = nn.Linear(hidden, hidden)
+        self.policy = nn.Linear(hidden, n_actions)
+        self.value = nn.Linear(hidden, 1)
+        self.relu = nn.ReLU()
+
+    def forward(self, planes: torch.Tensor):
+        x = planes.reshape(planes.shape[0], -1).to(self.fc1.weight.dtype)
+        x = self.relu(self.fc1(x))
+        x = self.relu(self.fc2(x))
+        x = self.relu(self.fc3(x))
+        return self.policy(x), torch.tanh(self.value(x)).squeeze(-1)
+
+
+class _ResBlock(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.c1 = nn.Conv2d(ch, ch, 3, padding=1, bias=False)
+        self.b1 = nn.BatchNorm2d(ch)
+        self.c2 = nn.Conv2d(ch, ch, 3, padding=1, bias=False)
+        self.b2 = nn.BatchNorm2d(ch)
+
+    def forward(self, x):
+        y = torch.relu(self.b1(self.c1(x)))
+        y = self.b2(self.c2(y))
+        return torch.relu(x + y)
+
+
+class PolicyValueResNet(nn.Module):
+    """AlphaZero-style tower on [B, 2, 8, 8] planes."""
+
+    def __init__(self, channels: int = 64, blocks: int = 4, n_actions: int = N_ACTIONS):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv2d(2, channels, 3, padding=1, bias=False), nn.BatchNorm2d(channels), nn.ReLU())
+        self.tower = nn.Sequential(*[_ResBlock(channels) for _ in range(blocks)])
+        self.p_conv = nn.Sequential(nn.Conv2d(channels, 2, 1, bias=False), nn.BatchNorm2d(2), nn.ReLU())
+        self.p_fc = nn.Linear(2 * 64, n_actions)
+        self.v_conv = nn.Sequential(nn.Conv2d(channels, 1, 1, bias=False), nn.BatchNorm2d(1), nn.ReLU())
+        self.v_fc = nn.Sequential(nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 1))
+
+    def forward(self, planes: torch.Tensor):
+        x = planes.reshape(-1, 2, 8, 8).to(self.p_fc.weight.dtype)
+        x = self.tower(self.stem(x))
+        p = self.p_fc(self.p_conv(x).flatten(1))
+        v = torch.tanh(self.v_fc(self.v_conv(x).flatten(1))).squeeze(-1)
+        return p, v
+
+
+def make_net(kind: str = "mlp", game: str = "reversi", hidden: int = 256, channels: int = 64, blocks: int = 4,
+             seed: int | None = 0, device="cuda", dtype=torch.bfloat16) -> nn.Module:
+    """Random-init net (there are no checkpoints to load: the reference has no Reversi net and its
+    tic-tac-toe pickles are policy-only)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    if game == "ttt":
+        net = PolicyValueMLP(9, hidden, TTT_ACTIONS)  # 9 inputs: the reference's own canonical vector
+    elif kind == "mlp":
+        net = PolicyValueMLP(128, hidden, N_ACTIONS)
+    elif kind == "resnet":
+        net = PolicyValueResNet(channels, blocks, N_ACTIONS)
+    else:
+        raise ValueError(f"unknown net kind {kind!r}")
+    return net.to(device=device, dtype=dtype).eval()
+
+
+def matmul_flops_per_position(net: nn.Module) -> int:
+    """2 * MACs of the Linear / Conv2d layers for one position (SURVEY.md 8d 'Net flops')."""
+    total = 0
+    for m in net.modules():
+        if isinstance(m, nn.Linear):
+            total += 2 * m.in_features * m.out_features
+        elif isinstance(m, nn.Conv2d):
+            k = m.kernel_size[0] * m.kernel_size[1]
+            total += 2 * 64 * m.in_channels * m.out_channels * k // m.groups
+    return total

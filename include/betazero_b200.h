@@ -197,6 +197,57 @@ int bz_mcts_best_action(const bz_tree_pools *pools, uint8_t *action, bz_stream_t
 int bz_hash_eval(const uint64_t *me, const uint64_t *opp, uint64_t salt, int n_actions, float *prior_w,
                  float *value, int64_t n, bz_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Lockstep self-play driver state (the batched form of the reference episode loops,
+ * reversi_terminal.py:16-38: search -> move or pass -> terminal test -> flip player; finished
+ * games are scored with get_score (reversi_board.py:67-76), flushed to the replay buffer and
+ * their slot restarts from the start position with a fresh game id).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bz_selfplay_state {
+    int32_t n_games;    /* slots == trees of the pools used with it */
+    int32_t board_size; /* 4, 6, 8 */
+    int32_t max_plies;  /* history rows per slot (>= 2*cells; 128 for 8x8) */
+    int32_t temp_plies; /* plies < temp_plies sample the move ~ visit counts (Philox keyed by
+                           seed, game id, ply); later plies take the most visited action */
+    uint64_t seed;
+    int64_t id_stride;  /* a restarted slot continues with game_id + id_stride */
+    int64_t replay_cap; /* records */
+    /* per slot [n_games] */
+    uint64_t *me, *opp; /* current position, mover-relative */
+    int8_t *player;     /* absolute side to move: +1 = X, -1 = O */
+    int32_t *ply;
+    int64_t *game_id;
+    /* per slot history [n_games * max_plies] (pi: [.., 65]) */
+    uint64_t *hist_me, *hist_opp;
+    int8_t *hist_player;
+    uint8_t *hist_action;
+    float *hist_pi;
+    /* replay buffer [replay_cap] (pi: [replay_cap, 65]); z = game result for the record's mover */
+    uint64_t *rp_me, *rp_opp;
+    float *rp_pi;
+    int8_t *rp_z;
+    int64_t *rp_game;
+    int16_t *rp_ply;
+    /* device counters, uint64 [8]: 0 replay records written, 1 plies played, 2 O wins, 3 draws,
+     * 4 X wins, 5 records dropped (replay full), 6 games finished, 7 reserved */
+    unsigned long long *counters;
+} bz_selfplay_state;
+
+/* All slots to the start position (ReversiBoard.__init__, reversi_board.py:9-11; X moves first,
+ * reversi_terminal.py:14); slot s gets game id first_game_id + s.  Zeroes the counters. */
+int bz_selfplay_init(const bz_selfplay_state *st, int64_t first_game_id, bz_stream_t stream);
+
+/* One lockstep ply for every slot, from the finished search in `pools` (tree s <-> slot s):
+ * pi = root visit counts / total, action = sampled or most visited (lowest id on ties), record
+ * to history, apply (K2), terminal test (K3); a finished game is flushed to the replay buffer
+ * with z and the slot restarts.  action_out (uint8 [n_games]) may be NULL. */
+int bz_selfplay_advance(const bz_selfplay_state *st, const bz_tree_pools *pools, uint8_t *action_out,
+                        bz_stream_t stream);
+
+/* Philox4x32-10 of (seed, game_id, ply): the u32 the move sampler draws (for tests). */
+int bz_philox_u32(uint64_t seed, const int64_t *game_id, const int32_t *ply, uint32_t *out, int64_t n,
+                  bz_stream_t stream);
+
 /* INT32 issue-rate microbenchmark (LOP3 / SHF / IADD3 mix) for the env roofline denominator:
  * every thread runs `iters` rounds of 64 dependent-chain-free integer instructions x 4 chains.
  * sink: device uint32 [1].  Returns the number of integer instructions per thread in *ops_per_thread

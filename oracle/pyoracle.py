@@ -86,6 +86,11 @@ def _declare(L):
     L.orc_mcts_search_hash.argtypes = [C.c_int, C.c_int, C.c_float, C.c_uint64, _pu64, _pu64, C.c_int64, C.c_int,
                                        _pi32, _pf, _pf, _pi64]
     L.orc_num_threads.restype = C.c_int
+    _pp = C.POINTER(C.c_void_p)
+    L.orc_mcts_batch_reset_wire.argtypes = [_pp, C.c_int64, _pu64, _pu64]
+    L.orc_mcts_batch_select.argtypes = [_pp, C.c_int64, _pu64, _pu64, _pu8, _pf]
+    L.orc_mcts_batch_expand_backup.argtypes = [_pp, C.c_int64, _pf, _pf, C.c_int]
+    L.orc_mcts_batch_root_counts.argtypes = [_pp, C.c_int64, _pi32, C.c_int]
 
 
 def _ptr(a: np.ndarray, ty):
@@ -358,3 +363,40 @@ def search_hash(me, opp, n_sims, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0)
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+class OracleForest:
+    """Many C trees stepped in lockstep (OpenMP over trees): the CPU baseline's counterpart of the
+    GPU's BatchedMCTS, usable with any evaluator (e.g. the same PyTorch net on the CPU)."""
+
+    def __init__(self, n, game=GAME_REVERSI, size=8, c_puct=1.25):
+        self.n, self.game = int(n), game
+        self.n_actions = 9 if game == GAME_TTT else 65
+        self._trees = [lib().orc_mcts_new(game, size, c_puct) for _ in range(self.n)]
+        self._arr = (C.c_void_p * self.n)(*self._trees)
+        self.leaf_me = np.zeros(self.n, np.uint64)
+        self.leaf_opp = np.zeros(self.n, np.uint64)
+        self.status = np.zeros(self.n, np.uint8)
+        self.planes = np.zeros((self.n, 2, 8, 8), np.float32)
+
+    def __del__(self):
+        for t in getattr(self, "_trees", []):
+            lib().orc_mcts_free(t)
+        self._trees = []
+
+    def reset(self, me, opp):
+        me, opp = _c(me, np.uint64), _c(opp, np.uint64)
+        lib().orc_mcts_batch_reset_wire(self._arr, self.n, _ptr(me, _pu64), _ptr(opp, _pu64))
+
+    def select(self):
+        lib().orc_mcts_batch_select(self._arr, self.n, _ptr(self.leaf_me, _pu64), _ptr(self.leaf_opp, _pu64),
+                                    _ptr(self.status, _pu8), _ptr(self.planes, _pf))
+
+    def expand_backup(self, w, v):
+        w, v = _c(w, np.float32), _c(v, np.float32)
+        lib().orc_mcts_batch_expand_backup(self._arr, self.n, _ptr(w, _pf), _ptr(v, _pf), self.n_actions)
+
+    def root_counts(self):
+        cnt = np.zeros((self.n, self.n_actions), np.int32)
+        lib().orc_mcts_batch_root_counts(self._arr, self.n, _ptr(cnt, _pi32), self.n_actions)
+        return cnt

@@ -80,7 +80,8 @@ def test_config2_one_million_boards_vs_oracle():
     # fused step: lowest legal move (or pass)
     k, act, m2, o2 = env.step_first_legal(me, opp)
     assert np.array_equal(env.to_host_u64(k), ref_mask)
-    low = np.where(ref_mask != 0, np.log2((ref_mask & (~ref_mask + np.uint64(1))).astype(np.float64)).astype(np.int64), 64)
+    lsb = np.maximum(ref_mask & (~ref_mask + np.uint64(1)), np.uint64(1)).astype(np.float64)  # exact: a power of two
+    low = np.where(ref_mask != 0, np.log2(lsb).astype(np.int64), 64)
     assert np.array_equal(act.cpu().numpy().astype(np.int64), low)
     rm, ro, rerr = po.apply(me_h, opp_h, low.astype(np.uint8))
     assert not rerr.any()
