@@ -11,7 +11,7 @@ from . import _lib  # noqa: F401
 __version__ = "0.1.0"
 
 
-def build(force: bool = False) -> str:
+def build_library(force: bool = False) -> str:
     """Compile the CUDA library in-tree (nvcc, sm_100a)."""
     from . import build as _b
 
