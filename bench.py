@@ -193,7 +193,8 @@ def run_b200(args):
 
     B, S = args.games, args.sims
     net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
-    sp = selfplay.BatchedSelfPlay(B, S, mcts.NetEvaluator(net), temp_plies=8, seed=1234, rank=rank, world=world,
+    evaluator = mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
+    sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
                                   graph_unroll=args.graph_unroll)
     sp.prepare()
     for _ in range(args.warmup):

@@ -21,13 +21,15 @@ class BzTreePools(C.Structure):
 
     _fields_ = [
         ("game", C.c_int32), ("board_size", C.c_int32), ("n_trees", C.c_int32), ("n_actions", C.c_int32),
-        ("edge_cap", C.c_int32), ("max_depth", C.c_int32), ("c_puct", C.c_float), ("reserved", C.c_int32),
-        ("root_me", ptr), ("root_opp", ptr), ("root_meta", ptr), ("edge_count", ptr), ("sim_count", ptr),
-        ("depth_sum", ptr), ("error", ptr),
-        ("edge_N", ptr), ("edge_W", ptr), ("edge_P", ptr), ("edge_meta", ptr), ("edge_me", ptr), ("edge_opp", ptr),
-        ("path", ptr), ("path_len", ptr), ("leaf_me", ptr), ("leaf_opp", ptr), ("leaf_mask", ptr),
-        ("leaf_status", ptr), ("leaf_value", ptr), ("leaf_planes", ptr),
+        ("arena_units", C.c_int32), ("max_depth", C.c_int32), ("c_puct", C.c_float), ("prior_mode", C.c_int32),
+        ("eval_stride", C.c_int32), ("reserved", C.c_int32),
+        ("root_me", ptr), ("root_opp", ptr), ("root_meta", ptr), ("arena_used", ptr), ("edge_count", ptr),
+        ("sim_count", ptr), ("depth_sum", ptr), ("error", ptr),
+        ("arena", ptr),
+        ("path", ptr), ("path_len", ptr), ("leaf_parent", ptr), ("leaf_me", ptr), ("leaf_opp", ptr),
+        ("leaf_mask", ptr), ("leaf_status", ptr), ("leaf_action", ptr), ("leaf_value", ptr), ("leaf_planes", ptr),
     ]
+    N_SCALARS = 10
 
 
 class BzSelfplayState(C.Structure):
@@ -66,6 +68,7 @@ SIGNATURES = {
     "bz_mcts_expand_backup": [_PP, ptr, ptr, ptr],
     "bz_mcts_step": [_PP, ptr, ptr, ptr],
     "bz_mcts_root_policy": [_PP, ptr, ptr, ptr, ptr],
+    "bz_mcts_root_edges": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_best_action": [_PP, ptr, ptr],
     "bz_hash_eval": [ptr, ptr, _U64, _INT, ptr, ptr, _I64, ptr],
     "bz_selfplay_init": [_SP, _I64, ptr],

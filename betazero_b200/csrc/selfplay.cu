@@ -51,16 +51,16 @@ __global__ void __launch_bounds__(kThreads)
     // root statistics: lane i holds edge i (ascending action id); a 33rd edge is read uniformly
     const uint32_t rmeta = P.root_meta[s];
     const int n = (int)((rmeta >> BZ_META_N_SHIFT) & 63u);
-    const int64_t base = (int64_t)s * P.edge_cap + (rmeta >> BZ_META_OFF_SHIFT);
+    const uint32_t *blk = P.arena + (int64_t)s * P.arena_units * 8 + (int64_t)(rmeta >> BZ_META_OFF_SHIFT) * 8;
     int Ne = 0, N32 = 0;
     unsigned act = 127u, act32 = 127u;
     if (lane < n) {
-        Ne = P.edge_N[base + lane];
-        act = P.edge_meta[base + lane] & 127u;
+        Ne = (int)blk[BZ_NODE_HEADER_WORDS + lane];
+        act = blk[BZ_NODE_HEADER_WORDS + 3 * n + lane] & 127u;
     }
     if (n > 32) {
-        N32 = P.edge_N[base + 32];
-        act32 = P.edge_meta[base + 32] & 127u;
+        N32 = (int)blk[BZ_NODE_HEADER_WORDS + 32];
+        act32 = blk[BZ_NODE_HEADER_WORDS + 3 * n + 32] & 127u;
     }
     const int total = __reduce_add_sync(kFull, Ne) + N32;
     const int ply = S.ply[s];
@@ -203,7 +203,7 @@ int bz_selfplay_advance(const bz_selfplay_state *st, const bz_tree_pools *pools,
     int rc = check_state(st);
     if (rc != BZ_OK) return rc;
     if (!pools || pools->game != BZ_GAME_REVERSI || pools->n_trees != st->n_games || pools->board_size != st->board_size ||
-        !pools->root_meta || !pools->edge_N || !pools->edge_meta)
+        !pools->root_meta || !pools->arena)
         return BZ_ERR_ARG;
     if (st->n_games == 0) return BZ_OK;
     selfplay_advance_kernel<<<(st->n_games + kWarpsPerCta - 1) / kWarpsPerCta, kThreads, 0, as_stream(stream)>>>(

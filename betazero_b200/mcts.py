@@ -20,35 +20,41 @@ from ._lib import BzTreePools
 
 GAME_REVERSI, GAME_TTT = 0, 1
 LEAF_EVAL, LEAF_TERMINAL, LEAF_ERROR = 0, 1, 2
-MAX_EDGE_CAP = 0x7FFF0
-_MAX_BRANCH = {GAME_REVERSI: 33, GAME_TTT: 9}  # 33 = most legal moves of any 8x8 Reversi position
+PRIOR_WEIGHTS, PRIOR_LOGITS_BF16 = 0, 1
+MAX_ARENA_UNITS = 0x7FFF0
+_NODE_UNITS = {GAME_REVERSI: 18, GAME_TTT: 6}  # worst-case node block: 33 (8x8 Reversi) / 9 edges
 
 
 class TreePools:
-    """Caller-owned SoA pools for ``n_trees`` concurrent trees (``bz_tree_pools``).
+    """Caller-owned pools for ``n_trees`` concurrent trees (``bz_tree_pools``): one arena of node
+    blocks per tree plus the per-tree pending-leaf records, all resident in HBM.
 
     ``sims_cap``: the largest number of iterations a search will run between resets; every
-    iteration expands at most one node, and a node has at most 33 (Reversi) / 9 (TTT) edges, so
-    ``edge_cap = sims_cap * max_branch`` can never overflow.  A smaller ``edge_cap`` may be passed
-    (mean branching is ~8-10); overflow is detected and raised, never silent.
+    iteration expands at most one node and a node block takes at most 18 (Reversi) / 6 (TTT)
+    32-byte units, so ``arena_units = sims_cap * that`` can never overflow.  A smaller
+    ``arena_units`` may be passed (mean branching is ~8-10); overflow is detected and raised,
+    never silent.
     """
 
     def __init__(self, n_trees: int, sims_cap: int, game: int = GAME_REVERSI, board_size: int = 8,
-                 c_puct: float = 1.25, edge_cap: int | None = None, max_depth: int | None = None, device="cuda"):
+                 c_puct: float = 1.25, arena_units: int | None = None, max_depth: int | None = None,
+                 prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, device="cuda"):
         if game not in (GAME_REVERSI, GAME_TTT):
             raise ValueError("game must be GAME_REVERSI or GAME_TTT")
         self.game, self.board_size = game, (3 if game == GAME_TTT else board_size)
         self.n_trees, self.sims_cap = int(n_trees), int(sims_cap)
         self.n_actions = 9 if game == GAME_TTT else 65
         self.c_puct = float(c_puct)
-        if edge_cap is None:
-            edge_cap = min(self.sims_cap * _MAX_BRANCH[game], MAX_EDGE_CAP)
-        if edge_cap > MAX_EDGE_CAP:
-            raise ValueError(f"edge_cap {edge_cap} exceeds {MAX_EDGE_CAP}")
-        self.edge_cap = int(edge_cap)
+        if arena_units is None:
+            arena_units = min(max(self.sims_cap, 1) * _NODE_UNITS[game], MAX_ARENA_UNITS)
+        arena_units = max(int(arena_units), 18)
+        if arena_units > MAX_ARENA_UNITS:
+            raise ValueError(f"arena_units {arena_units} exceeds {MAX_ARENA_UNITS}")
+        self.arena_units = arena_units
         self.max_depth = int(max_depth or (16 if game == GAME_TTT else 128))
+        self.prior_mode, self.eval_stride = int(prior_mode), int(eval_stride)
         self.device = torch.device(device)
-        B, E, D = self.n_trees, self.n_trees * self.edge_cap, self.n_trees * self.max_depth
+        B = max(self.n_trees, 1)
         dev = self.device
 
         def e(n, dt):
@@ -56,76 +62,149 @@ class TreePools:
 
         self.root_me, self.root_opp = e(B, torch.int64), e(B, torch.int64)
         # valid "empty tree" state from the start, so no kernel ever walks uninitialised memory
-        self.root_meta = torch.full((max(B, 1),), -8192, dtype=torch.int32, device=dev)  # meta(UNEXPANDED)
-        self.edge_count, self.sim_count = torch.zeros(max(B, 1), dtype=torch.int32, device=dev), e(B, torch.int32)
-        self.depth_sum, self.error = e(B, torch.int32), torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
-        self.edge_N, self.edge_W, self.edge_P = e(E, torch.int32), e(E, torch.float32), e(E, torch.float32)
-        self.edge_meta = e(E, torch.int32)
-        self.edge_me, self.edge_opp = e(E, torch.int64), e(E, torch.int64)
-        self.path, self.path_len = e(D, torch.int32), e(B, torch.int32)
+        self.root_meta = torch.full((B,), -8192, dtype=torch.int32, device=dev)  # meta(UNEXPANDED)
+        self.arena_used = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.edge_count, self.sim_count = torch.zeros(B, dtype=torch.int32, device=dev), e(B, torch.int32)
+        self.depth_sum, self.error = e(B, torch.int32), torch.zeros(B, dtype=torch.int32, device=dev)
+        self.arena = e(B * self.arena_units * 8, torch.int32)
+        self.path, self.path_len = e(B * self.max_depth * 4, torch.int32), torch.zeros(B, dtype=torch.int32, device=dev)
+        self.leaf_parent = e(B, torch.int32)
         self.leaf_me, self.leaf_opp, self.leaf_mask = e(B, torch.int64), e(B, torch.int64), e(B, torch.int64)
-        self.leaf_status = torch.full((max(B, 1),), LEAF_ERROR, dtype=torch.uint8, device=dev)
+        self.leaf_status = torch.full((B,), LEAF_ERROR, dtype=torch.uint8, device=dev)
+        self.leaf_action = e(B, torch.uint8)
         self.leaf_value = e(B, torch.float32)
         if game == GAME_TTT:
-            self.leaf_planes = torch.zeros((max(B, 1), 9), dtype=torch.bfloat16, device=dev)
+            self.leaf_planes = torch.zeros((B, 9), dtype=torch.bfloat16, device=dev)
         else:
-            self.leaf_planes = torch.zeros((max(B, 1), 2, 8, 8), dtype=torch.bfloat16, device=dev)
+            self.leaf_planes = torch.zeros((B, 2, 8, 8), dtype=torch.bfloat16, device=dev)
         s = BzTreePools()
-        s.game, s.board_size, s.n_trees, s.n_actions = game, self.board_size if game == GAME_REVERSI else 8, B, self.n_actions
-        s.edge_cap, s.max_depth, s.c_puct, s.reserved = self.edge_cap, self.max_depth, self.c_puct, 0
-        for name, _ in BzTreePools._fields_[8:]:
+        s.game, s.board_size, s.n_trees, s.n_actions = game, (self.board_size if game == GAME_REVERSI else 8), self.n_trees, self.n_actions
+        s.arena_units, s.max_depth, s.c_puct, s.prior_mode = self.arena_units, self.max_depth, self.c_puct, self.prior_mode
+        s.eval_stride, s.reserved = self.eval_stride, 0
+        for name, _ in BzTreePools._fields_[BzTreePools.N_SCALARS:]:
             setattr(s, name, getattr(self, name).data_ptr())
         self.c_struct = s
         self._ref = C.byref(s)
 
+    def set_prior_mode(self, mode: int, eval_stride: int = 0) -> None:
+        self.prior_mode, self.eval_stride = int(mode), int(eval_stride)
+        self.c_struct.prior_mode, self.c_struct.eval_stride = self.prior_mode, self.eval_stride
+
     # bytes of HBM held by the pools
     def nbytes(self) -> int:
-        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n, _ in BzTreePools._fields_[8:])
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size()
+                   for n, _ in BzTreePools._fields_[BzTreePools.N_SCALARS:])
 
 
 class HashEvaluator:
     """Parity-mode evaluator: the integer-hash pseudo-net (``bz_hash_eval``), exact in fp32 and
-    identical to oracle/mcts_ref.py:hash_eval."""
+    identical to oracle/mcts_ref.py:hash_eval.  Produces prior WEIGHTS (BZ_PRIOR_WEIGHTS)."""
+
+    prior_mode = PRIOR_WEIGHTS
 
     def __init__(self, salt: int = 0):
         self.salt = int(salt)
 
-    def __call__(self, pools: TreePools, out_w: torch.Tensor, out_v: torch.Tensor) -> None:
+    def bind(self, pools: "TreePools"):
+        B, A = max(pools.n_trees, 1), pools.n_actions
+        self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
+        self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
+        return self.out, self.value
+
+    def __call__(self, pools: "TreePools") -> None:
         L = _lib.load()
         _lib.check(L.bz_hash_eval(_lib.dptr(pools.leaf_me), _lib.dptr(pools.leaf_opp), self.salt, pools.n_actions,
-                                  _lib.dptr(out_w), _lib.dptr(out_v), pools.n_trees, _lib.stream_ptr()),
+                                  _lib.dptr(self.out), _lib.dptr(self.value), pools.n_trees, _lib.stream_ptr()),
                    "bz_hash_eval")
 
 
+class WeightsEvaluator:
+    """Evaluator fed from outside (tests / replaying recorded priors): fill ``out`` and ``value``."""
+
+    prior_mode = PRIOR_WEIGHTS
+
+    def bind(self, pools: "TreePools"):
+        B, A = max(pools.n_trees, 1), pools.n_actions
+        self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
+        self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
+        return self.out, self.value
+
+    def __call__(self, pools: "TreePools") -> None:
+        pass
+
+
 class NetEvaluator:
-    """PyTorch policy/value net on the gathered bf16 leaf planes.  The net returns
-    ``(logits [B, A], value [B])``; prior weights are ``softmax(logits)`` in fp32 (the tree kernel
-    renormalises them over the legal actions)."""
+    """PyTorch policy/value net on the gathered bf16 leaf planes, parity-friendly form: the net
+    returns ``(logits [B, A], value [B])``, prior weights are ``softmax(logits)`` in fp32 and the
+    tree kernel renormalises them over the legal actions (BZ_PRIOR_WEIGHTS).  The weights of a
+    search can be recorded and replayed into the oracle."""
+
+    prior_mode = PRIOR_WEIGHTS
 
     def __init__(self, net: torch.nn.Module):
         self.net = net
 
+    def bind(self, pools: "TreePools"):
+        B, A = max(pools.n_trees, 1), pools.n_actions
+        self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
+        self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
+        return self.out, self.value
+
     @torch.no_grad()
-    def __call__(self, pools: TreePools, out_w: torch.Tensor, out_v: torch.Tensor) -> None:
+    def __call__(self, pools: "TreePools") -> None:
         logits, value = self.net(pools.leaf_planes)
-        torch.softmax(logits.float(), dim=-1, out=out_w)
-        out_v.copy_(value.reshape(-1))
+        torch.softmax(logits.float(), dim=-1, out=self.out)
+        self.value.copy_(value.reshape(-1))
+
+
+class FusedNetEvaluator:
+    """Throughput form: the net's ``forward_raw(planes) -> bf16 [B, stride]`` (policy logits in
+    columns 0..A-1, pre-tanh value in column A) is handed to the tree kernel as is; the kernel does
+    the legal-move softmax and the tanh itself (BZ_PRIOR_LOGITS_BF16), so an iteration is the net's
+    GEMMs plus ONE tree kernel."""
+
+    prior_mode = PRIOR_LOGITS_BF16
+
+    def __init__(self, net: torch.nn.Module):
+        if not hasattr(net, "forward_raw"):
+            raise TypeError("FusedNetEvaluator needs a net with forward_raw()")
+        self.net = net
+
+    def bind(self, pools: "TreePools"):
+        B = max(pools.n_trees, 1)
+        self.stride = int(self.net.raw_width)
+        self.out = torch.zeros((B, self.stride), dtype=torch.bfloat16, device=pools.device)
+        self.value = torch.zeros(1, dtype=torch.float32, device=pools.device)  # unused in this mode
+        pools.set_prior_mode(PRIOR_LOGITS_BF16, self.stride)
+        self.refresh()
+        return self.out, self.value
+
+    def refresh(self) -> None:
+        """rebuild the net's fused inference weights (after a weight update / broadcast)"""
+        if hasattr(self.net, "prepare_inference"):
+            self.net.prepare_inference()
+
+    @torch.no_grad()
+    def __call__(self, pools: "TreePools") -> None:
+        self.net.forward_raw(pools.leaf_planes, out=self.out)
 
 
 class BatchedMCTS:
     """Lockstep search over all trees of a :class:`TreePools`.
 
-    ``evaluator(pools, out_w, out_v)`` must be stream-ordered GPU work that reads
-    ``pools.leaf_planes`` (or ``leaf_me/leaf_opp``) and fills ``out_w`` float32 [B, A] (>= 0) and
-    ``out_v`` float32 [B]; it is captured into the CUDA graph together with the tree kernel.
+    ``evaluator.bind(pools)`` returns the (eval_out, value) buffers the tree kernels read;
+    ``evaluator(pools)`` must be stream-ordered GPU work that reads ``pools.leaf_planes`` (or
+    ``leaf_me/leaf_opp``) and fills them; it is captured into the CUDA graph with the tree kernel.
     """
 
     def __init__(self, pools: TreePools, evaluator, use_graph: bool = True, graph_unroll: int = 16, fused: bool = True):
         self.pools, self.evaluator = pools, evaluator
         self.use_graph, self.unroll, self.fused = bool(use_graph), int(graph_unroll), bool(fused)
         B, A = max(pools.n_trees, 1), pools.n_actions
-        self.prior_w = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
-        self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
+        if evaluator is None:
+            evaluator = self.evaluator = WeightsEvaluator()
+        self.prior_w, self.value = evaluator.bind(pools)  # eval_out / value buffers the kernels read
+        pools.set_prior_mode(evaluator.prior_mode, getattr(evaluator, "stride", 0))
         self.counts = torch.zeros((B, A), dtype=torch.int32, device=pools.device)
         self.pi = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
         self.q = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
@@ -147,7 +226,7 @@ class BatchedMCTS:
         self.launches += 1
 
     def evaluate(self) -> None:
-        self.evaluator(self.pools, self.prior_w, self.value)
+        self.evaluator(self.pools)
 
     def expand_backup(self) -> None:
         _lib.check(self._L.bz_mcts_expand_backup(self.pools._ref, _lib.dptr(self.prior_w), _lib.dptr(self.value),
@@ -250,8 +329,8 @@ class BatchedMCTS:
         err = self.pools.error[: self.pools.n_trees]
         if self.pools.n_trees and bool(err.any().item()):
             codes = sorted(set(err[err != 0].tolist()))
-            raise _lib.BzError(f"tree pool overflow (codes {codes}: 1 = edge pool, 2 = path depth); "
-                               "enlarge edge_cap / max_depth")
+            raise _lib.BzError(f"tree pool overflow (codes {codes}: 1 = arena, 2 = path depth); "
+                               "enlarge arena_units / max_depth")
 
     def stats(self) -> dict:
         """mean path depth d and mean edges per expanded node b of the last search (roofline model)."""
@@ -259,4 +338,17 @@ class BatchedMCTS:
         sims = int(p.sim_count[: p.n_trees].sum().item())
         depth = int(p.depth_sum[: p.n_trees].sum().item())
         edges = int(p.edge_count[: p.n_trees].sum().item())
-        return {"sims": sims, "mean_depth": depth / max(sims, 1), "edges": edges}
+        units = int(p.arena_used[: p.n_trees].sum().item())
+        return {"sims": sims, "mean_depth": depth / max(sims, 1), "edges": edges, "arena_units": units}
+
+    def root_edges(self):
+        """(N int32, W float32, P float32) of the root edges scattered by action, [B, A] each."""
+        p = self.pools
+        B, A = max(p.n_trees, 1), p.n_actions
+        N = torch.zeros((B, A), dtype=torch.int32, device=p.device)
+        W = torch.zeros((B, A), dtype=torch.float32, device=p.device)
+        P = torch.zeros((B, A), dtype=torch.float32, device=p.device)
+        _lib.check(self._L.bz_mcts_root_edges(p._ref, _lib.dptr(N), _lib.dptr(W), _lib.dptr(P), _lib.stream_ptr()),
+                   "bz_mcts_root_edges")
+        self.launches += 1
+        return N, W, P

@@ -29,6 +29,9 @@ class PolicyValueMLP(nn.Module):
         self.policy = nn.Linear(hidden, n_actions)
         self.value = nn.Linear(hidden, 1)
         self.relu = nn.ReLU()
+        self.n_actions = n_actions
+        self.raw_width = (n_actions + 1 + 7) // 8 * 8  # fused head, padded so the GEMM stays aligned
+        self._head = None
 
     def forward(self, planes: torch.Tensor):
         x = planes.reshape(planes.shape[0], -1).to(self.fc1.weight.dtype)
@@ -36,6 +39,33 @@ class PolicyValueMLP(nn.Module):
         x = self.relu(self.fc2(x))
         x = self.relu(self.fc3(x))
         return self.policy(x), torch.tanh(self.value(x)).squeeze(-1)
+
+    # -- inference fast path: 4 GEMM launches, bias+ReLU in the cuBLASLt epilogue, one fused head ----
+    @torch.no_grad()
+    def prepare_inference(self) -> None:
+        """(Re)build the fused policy+value head [raw_width, H]; call after every weight update."""
+        w = torch.zeros((self.raw_width, self.policy.in_features), dtype=self.policy.weight.dtype,
+                        device=self.policy.weight.device)
+        b = torch.zeros(self.raw_width, dtype=w.dtype, device=w.device)
+        A = self.n_actions
+        w[:A], w[A] = self.policy.weight, self.value.weight[0]
+        b[:A], b[A] = self.policy.bias, self.value.bias[0]
+        self._head = (w, b)
+        self._w = [m.weight.t() for m in (self.fc1, self.fc2, self.fc3)]
+
+    @torch.no_grad()
+    def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A."""
+        if self._head is None:
+            self.prepare_inference()
+        x = planes.reshape(planes.shape[0], -1)
+        x = torch._addmm_activation(self.fc1.bias, x, self._w[0])
+        x = torch._addmm_activation(self.fc2.bias, x, self._w[1])
+        x = torch._addmm_activation(self.fc3.bias, x, self._w[2])
+        hw, hb = self._head
+        if out is None:
+            return torch.addmm(hb, x, hw.t())
+        return torch.addmm(hb, x, hw.t(), out=out)
 
 
 class _ResBlock(nn.Module):

@@ -24,11 +24,11 @@ N_ACTIONS = 65
 class BatchedSelfPlay:
     def __init__(self, n_games: int, n_sims: int, evaluator, board_size: int = 8, c_puct: float = 1.25,
                  temp_plies: int = 0, seed: int = 0, replay_cap: int | None = None, rank: int = 0, world: int = 1,
-                 edge_cap: int | None = None, use_graph: bool = True, graph_unroll: int = 16, device="cuda"):
+                 arena_units: int | None = None, use_graph: bool = True, graph_unroll: int = 16, device="cuda"):
         self.n_games, self.n_sims, self.board_size = int(n_games), int(n_sims), int(board_size)
         self.rank, self.world = int(rank), int(world)
         self.device = torch.device(device)
-        self.pools = TreePools(n_games, n_sims, board_size=board_size, c_puct=c_puct, edge_cap=edge_cap, device=device)
+        self.pools = TreePools(n_games, n_sims, board_size=board_size, c_puct=c_puct, arena_units=arena_units, device=device)
         self.mcts = BatchedMCTS(self.pools, evaluator, use_graph=use_graph, graph_unroll=graph_unroll)
         self.max_plies = 128
         B, H = max(self.n_games, 1), max(self.n_games, 1) * self.max_plies

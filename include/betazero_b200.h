@@ -115,51 +115,79 @@ int bz_ttt_terminal(const uint16_t *x, const uint16_t *o, uint8_t *over, int8_t 
  * (int64)tree * edge_cap.
  * ---------------------------------------------------------------------------------------- */
 
-/* edge_meta layout: bits 0..6 action, bits 7..12 number of edges of the child node (0 = child
- * not a normal node), bits 13..31 child's first edge (tree-local).  With child_n == 0 the
- * offset field holds BZ_META_UNEXPANDED or BZ_META_TERMINAL + {0,1,2} for a terminal child
- * worth {-1, 0, +1} to ITS side to move. */
+/* Tree storage.  Each tree owns an ARENA of 32-bit words; an expanded node is one contiguous,
+ * 32-byte aligned NODE BLOCK inside it, SoA within the block so that lane i of the owning warp
+ * reads edge i of every field with one coalesced access and a whole node costs one short burst
+ * of adjacent DRAM sectors:
+ *
+ *     word 0..1  me      (uint64, board of the node for its mover)
+ *     word 2..3  opp
+ *     word 4     n       (number of edges, 1..33)
+ *     word 5..7  reserved
+ *     word 8      .. 8+n-1    N[n]     int32   visit counts
+ *     word 8+n    .. 8+2n-1   W[n]     float32 total value
+ *     word 8+2n   .. 8+3n-1   P[n]     float32 prior
+ *     word 8+3n   .. 8+4n-1   meta[n]  uint32  action + child reference
+ *     (padded to a multiple of 8 words)
+ *
+ * meta: bits 0..6 action, bits 7..12 number of edges of the child (0 = child is not a normal
+ * node), bits 13..31 the child's block offset in 8-word units.  With child_n == 0 the offset
+ * field holds BZ_META_UNEXPANDED, or BZ_META_TERMINAL + {0,1,2} for a terminal child worth
+ * {-1, 0, +1} to ITS side to move.  Because an edge carries its child's (offset, n), one level of
+ * the PUCT descent is a single round of dependent loads. */
+#define BZ_NODE_HEADER_WORDS 8
 #define BZ_META_OFF_SHIFT 13
 #define BZ_META_N_SHIFT 7
 #define BZ_META_UNEXPANDED 0x7FFFFu
 #define BZ_META_TERMINAL 0x7FFF0u
-#define BZ_MAX_EDGE_CAP 0x7FFF0
+#define BZ_MAX_ARENA_UNITS 0x7FFF0 /* 8-word units per tree (16.7 MB) */
+#define BZ_MAX_NODE_UNITS 18       /* worst case: 33 edges -> 8 + 132 words -> 18 units */
 
 /* leaf_status values */
-#define BZ_LEAF_EVAL 0     /* needs the evaluator's (prior weights, value) */
+#define BZ_LEAF_EVAL 0     /* needs the evaluator's output */
 #define BZ_LEAF_TERMINAL 1 /* game over at the leaf: value known, evaluator output ignored */
-#define BZ_LEAF_ERROR 2    /* pool overflow; tree flagged in `error`, iteration skipped */
+#define BZ_LEAF_ERROR 2    /* pool overflow / no pending leaf; iteration skipped */
+
+/* how bz_mcts_expand_backup / bz_mcts_step read the evaluator's output */
+#define BZ_PRIOR_WEIGHTS 0 /* eval_out: float32 [n_trees, n_actions] weights >= 0, value: float32 [n_trees].
+                              P = w / sum over legal (ascending action order; sum 0 -> uniform).
+                              The parity mode: bit-exact against the oracle. */
+#define BZ_PRIOR_LOGITS_BF16 1 /* eval_out: bf16 [n_trees, eval_stride] raw network output: columns
+                              0..n_actions-1 policy logits, column n_actions the pre-tanh value.
+                              The kernel computes the softmax over the LEGAL actions and tanh itself
+                              (fast path: no softmax / cast / copy launches); `value` is ignored. */
 
 typedef struct bz_tree_pools {
-    int32_t game;       /* BZ_GAME_REVERSI / BZ_GAME_TTT */
-    int32_t board_size; /* Reversi: 4, 6, 8 */
+    int32_t game;        /* BZ_GAME_REVERSI / BZ_GAME_TTT */
+    int32_t board_size;  /* Reversi: 4, 6, 8 */
     int32_t n_trees;
-    int32_t n_actions; /* 65 / 9: row stride of prior_w, visit_counts, pi */
-    int32_t edge_cap;  /* edges per tree (<= BZ_MAX_EDGE_CAP); worst case 33 per expanded node */
-    int32_t max_depth; /* path capacity per tree */
+    int32_t n_actions;   /* 65 / 9: row length of weight / count / pi rows */
+    int32_t arena_units; /* 8-word units per tree (<= BZ_MAX_ARENA_UNITS); 18 per iteration never overflows */
+    int32_t max_depth;   /* path capacity per tree */
     float c_puct;
+    int32_t prior_mode;  /* BZ_PRIOR_WEIGHTS / BZ_PRIOR_LOGITS_BF16 */
+    int32_t eval_stride; /* row stride (elements) of eval_out in logits mode (>= n_actions + 1) */
     int32_t reserved;
     /* per tree [n_trees] */
     uint64_t *root_me, *root_opp;
-    uint32_t *root_meta;  /* like edge_meta, for the (virtual) edge into the root */
-    int32_t *edge_count;  /* bump allocator */
+    uint32_t *root_meta;  /* like an edge's meta, for the (virtual) edge into the root */
+    int32_t *arena_used;  /* bump allocator, in units */
+    int32_t *edge_count;  /* edges created since reset (mean children b of the roofline model) */
     int32_t *sim_count;   /* completed select/expand iterations since reset */
-    int32_t *depth_sum;   /* sum of path lengths of those iterations (mean depth d of the roofline model) */
-    int32_t *error;       /* sticky: 1 = edge pool overflow, 2 = path overflow */
-    /* per edge [n_trees * edge_cap] */
-    int32_t *edge_N;
-    float *edge_W;
-    float *edge_P;
-    uint32_t *edge_meta;
-    uint64_t *edge_me, *edge_opp; /* board AFTER the edge, for the child's mover (set on expansion) */
+    int32_t *depth_sum;   /* sum of path lengths of those iterations (mean depth d) */
+    int32_t *error;       /* sticky: 1 = arena overflow, 2 = path overflow */
+    /* the arenas: uint32 [n_trees * arena_units * 8] */
+    uint32_t *arena;
     /* pending leaf, per tree */
-    int32_t *path;      /* [n_trees * max_depth] tree-local edge indices, root first */
-    int32_t *path_len;  /* [n_trees] */
+    uint32_t *path;        /* [n_trees * max_depth * 4] records {word index of N, n, N, W bits}, root first */
+    int32_t *path_len;     /* [n_trees] */
+    int32_t *leaf_parent;  /* arena word index of the meta of the edge into the leaf (-1: the leaf is the root) */
     uint64_t *leaf_me, *leaf_opp;
-    uint64_t *leaf_mask; /* legal cells of the leaf's mover (0 with status EVAL = the mover must pass) */
+    uint64_t *leaf_mask;   /* legal cells of the leaf's mover (0 with status EVAL = the mover must pass) */
     uint8_t *leaf_status;
-    float *leaf_value;  /* terminal value for the leaf's mover */
-    void *leaf_planes;  /* bf16 [n_trees, 2, 8, 8] canonical planes of the leaf (K6) */
+    uint8_t *leaf_action;  /* action of the edge into the leaf */
+    float *leaf_value;     /* terminal value for the leaf's mover */
+    void *leaf_planes;     /* bf16 [n_trees, 2, 8, 8] canonical planes of the leaf (K6); TTT: [n_trees, 9] */
 } bz_tree_pools;
 
 /* Empty every tree and set its root position (mover-relative). */
@@ -173,15 +201,18 @@ int bz_mcts_select(const bz_tree_pools *pools, bz_stream_t stream);
 /* K6 on its own: re-pack leaf_me/leaf_opp into leaf_planes (select already does this). */
 int bz_mcts_gather(const bz_tree_pools *pools, bz_stream_t stream);
 
-/* K7: expand the pending leaf with priors = prior_w renormalised over its legal actions
- * (prior_w: float32 [n_trees, n_actions], >= 0; if the legal weights sum to 0 the prior is
- * uniform) and back `value` (float32 [n_trees], for the leaf's mover) up the path.  Terminal
- * leaves back up their exact game result instead. */
-int bz_mcts_expand_backup(const bz_tree_pools *pools, const float *prior_w, const float *value,
+/* K7: expand the pending leaf with the evaluator's output (see prior_mode) and back the leaf
+ * value (for the leaf's mover) up the path: store-only, atomic-free, one lane per path edge.
+ * Terminal leaves back up their exact game result instead. */
+int bz_mcts_expand_backup(const bz_tree_pools *pools, const void *eval_out, const float *value,
                           bz_stream_t stream);
 
 /* K7+K5+K6 in one launch: finish iteration i with the evaluator's output, start iteration i+1. */
-int bz_mcts_step(const bz_tree_pools *pools, const float *prior_w, const float *value, bz_stream_t stream);
+int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *value, bz_stream_t stream);
+
+/* Read one tree's root edges back in action order (debug / tests): N, W, P scattered by action
+ * into rows of n_actions (zeros elsewhere).  Any output may be NULL. */
+int bz_mcts_root_edges(const bz_tree_pools *pools, int32_t *N, float *W, float *P, bz_stream_t stream);
 
 /* K8: root visit counts (int32 [n_trees, n_actions]), pi = N / sum N and q = W / N (float32,
  * same shape; either may be NULL), scattered by action, zeros elsewhere. */

@@ -24,20 +24,9 @@ def _search(me_h, opp_h, n_sims, salt, game=0, size=8, c_puct=1.25, **kw):
 
 
 def _root_W_P(s):
-    """pull root-edge W and P back, scattered by action"""
-    p = s.pools
-    B, A = p.n_trees, p.n_actions
-    meta = p.root_meta.cpu().numpy().view(np.uint32)
-    W = np.zeros((B, A), np.float32)
-    P = np.zeros((B, A), np.float32)
-    eW, eP, eM = p.edge_W.cpu().numpy(), p.edge_P.cpu().numpy(), p.edge_meta.cpu().numpy().view(np.uint32)
-    for t in range(B):
-        n, off = (meta[t] >> 7) & 63, meta[t] >> 13
-        for i in range(n):
-            e = t * p.edge_cap + off + i
-            W[t, eM[e] & 127] = eW[e]
-            P[t, eM[e] & 127] = eP[e]
-    return W, P
+    """root-edge W and P, scattered by action"""
+    _, W, P = s.root_edges()
+    return W.cpu().numpy(), P.cpu().numpy()
 
 
 @pytest.mark.parametrize("prefix", ["rev8_playout_s48", "rev8_start_s400", "rev8_pass_s64"])
@@ -194,12 +183,12 @@ def test_terminal_and_pass_roots():
     assert pi.cpu().numpy()[1, 64] == 1.0
 
 
-def test_edge_pool_overflow_is_detected():
+def test_arena_overflow_is_detected():
     from betazero_b200 import _lib, env, mcts
     from oracle import pyoracle as po
 
     me_h, opp_h = po.playout_boards(8, seed=1)
-    pools = mcts.TreePools(8, 64, edge_cap=40)
+    pools = mcts.TreePools(8, 64, arena_units=40)
     s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(0), use_graph=False)
     with pytest.raises(_lib.BzError, match="overflow"):
         s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 64)
@@ -210,12 +199,77 @@ def test_hash_eval_kernel_matches_oracle():
     from oracle import pyoracle as po
 
     me_h, opp_h = po.synthetic_boards(500, seed=21)
+    me_d, opp_d = env.to_device_u64(me_h), env.to_device_u64(opp_h)  # keep alive: raw pointers are passed
     for A in (9, 65):
         w = torch.empty((500, A), dtype=torch.float32, device="cuda")
         v = torch.empty(500, dtype=torch.float32, device="cuda")
-        _lib.check(_lib.load().bz_hash_eval(_lib.dptr(env.to_device_u64(me_h)), _lib.dptr(env.to_device_u64(opp_h)), 77, A,
+        _lib.check(_lib.load().bz_hash_eval(_lib.dptr(me_d), _lib.dptr(opp_d), 77, A,
                                             _lib.dptr(w), _lib.dptr(v), 500, _lib.stream_ptr()))
         w, v = w.cpu().numpy(), v.cpu().numpy()
         for i in range(0, 500, 7):
             rw, rv = po.hash_eval(me_h[i], opp_h[i], 77, A)
             assert np.array_equal(w[i], rw) and v[i] == rv
+
+
+def test_logits_mode_fused_softmax_and_tanh():
+    """BZ_PRIOR_LOGITS_BF16: the tree kernel does the legal-move softmax and tanh itself.  Floating
+    point with fast intrinsics, so tolerance-checked (1e-5 abs on priors) against numpy."""
+    from betazero_b200 import env, mcts
+    from oracle import pyoracle as po
+
+    B = 512
+    me_h, opp_h = po.playout_boards(B, seed=31)
+    pools = mcts.TreePools(B, 4, prior_mode=mcts.PRIOR_LOGITS_BF16, eval_stride=72)
+
+    class Raw:
+        prior_mode = mcts.PRIOR_LOGITS_BF16
+        stride = 72
+
+        def bind(self, pools):
+            g = torch.Generator(device="cuda").manual_seed(5)
+            self.out = (torch.randn((B, 72), device="cuda", generator=g) * 3).to(torch.bfloat16)
+            self.value = torch.zeros(1, device="cuda")
+            return self.out, self.value
+
+        def __call__(self, pools):
+            pass
+
+    ev = Raw()
+    s = mcts.BatchedMCTS(pools, ev, use_graph=False)
+    s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
+    s.run(2)  # iteration 1 expands the root, iteration 2 visits one child and backs its value up
+    N, W, P = (x.cpu().numpy() for x in s.root_edges())
+    logits = ev.out.float().cpu().numpy()
+    mask = po.legal_mask(me_h, opp_h)
+    for i in range(B):
+        legal = [a for a in range(64) if (int(mask[i]) >> a) & 1] or [64]
+        l = logits[i, legal].astype(np.float64)
+        p = np.exp(l - l.max())
+        p /= p.sum()
+        np.testing.assert_allclose(P[i, legal], p, atol=2e-6, rtol=1e-5)
+        assert P[i].sum() == pytest.approx(1.0, abs=1e-5) and N[i].sum() == 1
+        a = int(np.argmax(N[i]))
+        # the visited child was expanded from the same logits row; its value tanh(l[65]) came back negated
+        assert W[i, a] == pytest.approx(-np.tanh(logits[i, 65]), abs=1e-5) or abs(W[i, a]) == 1.0 or W[i, a] == 0.0
+
+
+def test_fused_net_evaluator_agrees_with_parity_evaluator():
+    """same net through the fast path (bf16 logits -> in-kernel softmax) and through the parity
+    path (fp32 softmax weights): root priors agree to bf16 precision and the searches are close"""
+    from betazero_b200 import env, mcts, net
+    from oracle import pyoracle as po
+
+    B, n_sims = 256, 64
+    me_h, opp_h = po.playout_boards(B, seed=77)
+    model = net.make_net("mlp", seed=3)
+    res = []
+    for ev in (mcts.NetEvaluator(model), mcts.FusedNetEvaluator(model)):
+        pools = mcts.TreePools(B, n_sims)
+        s = mcts.BatchedMCTS(pools, ev, use_graph=True, graph_unroll=8)
+        cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
+        _, _, P = s.root_edges()
+        res.append((cnt.cpu().numpy(), P.cpu().numpy()))
+    np.testing.assert_allclose(res[0][1], res[1][1], atol=2e-2)
+    assert (res[0][0].sum(1) == n_sims - 1).all() and (res[1][0].sum(1) == n_sims - 1).all()
+    same = (res[0][0].argmax(1) == res[1][0].argmax(1)).mean()
+    assert same > 0.8
