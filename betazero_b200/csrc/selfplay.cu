@@ -172,6 +172,55 @@ __global__ void __launch_bounds__(256)
     if (i < n) out[i] = philox_u32(seed, (uint64_t)game_id[i], (uint32_t)ply[i]);
 }
 
+
+// ---- replay augmentation: dihedral transforms of (board, pi) records --------------------------------
+// destination cell of source cell (r, c) on an n x n board under transform k (train.py:27-36)
+__host__ __device__ inline int sym_cell(int k, int r, int c, int n) {
+    const int m = n - 1;
+    int nr, nc;
+    switch (k) {
+        case 1: nr = m - r; nc = c; break;      // flip(dims=[0])
+        case 2: nr = r; nc = m - c; break;      // flip(dims=[1])
+        case 3: nr = m - c; nc = r; break;      // rot90 x1: new[i][j] = old[j][m-i]
+        case 4: nr = m - r; nc = m - c; break;  // rot90 x2
+        case 5: nr = c; nc = m - r; break;      // rot90 x3: new[i][j] = old[m-j][i]
+        case 6: nr = c; nc = r; break;          // transpose
+        case 7: nr = m - c; nc = m - r; break;  // anti-transpose
+        default: nr = r; nc = c; break;
+    }
+    return nr * 8 + nc;
+}
+
+__global__ void __launch_bounds__(256)
+    symmetry_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, const float *__restrict__ pi,
+                    const uint8_t *__restrict__ sym, uint64_t *__restrict__ me_out, uint64_t *__restrict__ opp_out,
+                    float *__restrict__ pi_out, int64_t n, int size) {
+    const int64_t total = n * A;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = g / A;
+        const int a = (int)(g - i * A);
+        const int k = sym[i] & 7;
+        if (a == 64) {
+            pi_out[g] = pi[g];  // pass is invariant; this thread also transforms the two bitboards
+            uint64_t m = 0, o = 0;
+            for (uint64_t b = me[i]; b; b &= b - 1) {
+                const int s = __ffsll((long long)b) - 1;
+                m |= 1ull << sym_cell(k, s >> 3, s & 7, size);
+            }
+            for (uint64_t b = opp[i]; b; b &= b - 1) {
+                const int s = __ffsll((long long)b) - 1;
+                o |= 1ull << sym_cell(k, s >> 3, s & 7, size);
+            }
+            me_out[i] = m;
+            opp_out[i] = o;
+        } else {
+            const int r = a >> 3, c = a & 7;
+            if (r < size && c < size) pi_out[i * A + sym_cell(k, r, c, size)] = pi[g];
+            else pi_out[g] = 0.f;  // cells outside the board keep their (zero) slot
+        }
+    }
+}
+
 int check_state(const bz_selfplay_state *s) {
     if (!s) return BZ_ERR_ARG;
     if (!(s->board_size == 4 || s->board_size == 6 || s->board_size == 8)) return BZ_ERR_ARG;
@@ -208,6 +257,19 @@ int bz_selfplay_advance(const bz_selfplay_state *st, const bz_tree_pools *pools,
     if (st->n_games == 0) return BZ_OK;
     selfplay_advance_kernel<<<(st->n_games + kWarpsPerCta - 1) / kWarpsPerCta, kThreads, 0, as_stream(stream)>>>(
         *st, *pools, action_out, cell_mask(st->board_size));
+    return launch_rc();
+}
+
+int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi, const uint8_t *sym,
+                        uint64_t *me_out, uint64_t *opp_out, float *pi_out, int64_t n, int size,
+                        bz_stream_t stream) {
+    if (n < 0 || !(size == 4 || size == 6 || size == 8) ||
+        (n && (!me || !opp || !pi || !sym || !me_out || !opp_out || !pi_out)))
+        return BZ_ERR_ARG;
+    if (me == me_out || opp == opp_out || pi == pi_out) return BZ_ERR_ARG;  // not an in-place transform
+    if (n == 0) return BZ_OK;
+    symmetry_kernel<<<persistent_grid(n * A, 256, 8), 256, 0, as_stream(stream)>>>(me, opp, pi, sym, me_out, opp_out,
+                                                                                pi_out, n, size);
     return launch_rc();
 }
 

@@ -1,0 +1,95 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the GPU
+box, gloo in the CPU tests).
+
+Self-play needs NO data-path collective: games are independent units (the reference has no
+cross-game state: each ReversiTerminal / TicTacToeHeadless owns its board, reversi_terminal.py:11-14,
+tic_tac_toe.py:7-11), so rank r of W simply owns game ids ``{r*B + s + k*W*B}``.  Collectives
+appear only between iterations: ``broadcast_weights`` (new net from the training rank) and
+``gather_replay`` (replay shards to every rank / the training rank).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise from the torchrun environment.  Returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def game_ids(rank: int, world: int, slots: int, round_: int = 0) -> torch.Tensor:
+    """Global game ids owned by ``rank`` in restart round ``round_`` (matches bz_selfplay_init /
+    id_stride): slot s plays ``rank*slots + s + round_*world*slots``."""
+    return torch.arange(slots, dtype=torch.int64) + rank * slots + round_ * world * slots
+
+
+@torch.no_grad()
+def broadcast_weights(module: torch.nn.Module, src: int = 0) -> int:
+    """Broadcast every parameter and buffer of ``module`` from ``src`` as ONE flat buffer per dtype
+    (few MB: launch-latency bound, so one collective instead of one per tensor).  Returns bytes."""
+    if world_size() == 1:
+        return 0
+    tensors = [t for t in list(module.parameters()) + list(module.buffers()) if t.numel()]
+    total = 0
+    by_dtype: dict[torch.dtype, list[torch.Tensor]] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dt, ts in by_dtype.items():
+        flat = torch.cat([t.detach().reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for t in ts:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+        total += flat.numel() * flat.element_size()
+    return total
+
+
+def gather_replay(local: dict) -> dict:
+    """All-gather variable-length replay shards (dict of tensors with equal leading length) to
+    every rank, ordered by (game id, ply) so the result does not depend on the rank layout."""
+    keys = sorted(local)
+    n_local = int(local[keys[0]].shape[0])
+    if world_size() == 1:
+        out = {k: local[k] for k in keys}
+    else:
+        dev = local[keys[0]].device
+        counts = torch.zeros(world_size(), dtype=torch.int64, device=dev)
+        mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, mine)
+        n_max = int(counts.max().item())
+        out = {}
+        for k in keys:
+            t = local[k]
+            wire = t.to(torch.int32) if t.dtype in (torch.int16, torch.int8) else t  # gloo lacks some narrow types
+            pad = torch.zeros((n_max,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev)
+            pad[:n_local] = wire
+            buf = torch.empty((world_size() * n_max,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, pad)
+            parts = [buf[r * n_max: r * n_max + int(counts[r].item())] for r in range(world_size())]
+            out[k] = torch.cat(parts).to(t.dtype)
+    if "game" in out and "ply" in out and out["game"].numel():
+        order = torch.argsort(out["game"] * 1024 + out["ply"].to(torch.int64))
+        out = {k: v[order] for k, v in out.items()}
+    return out

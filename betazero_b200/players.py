@@ -1,0 +1,123 @@
+"""Drop-in players: ``get_move(board) -> (row, col)`` backed by the batched GPU MCTS.
+
+The reference defines the search interface as an ABC with one method
+(``ReversiPlayer.get_move`` src/reversi/players/reversi_players.py:5-8, ``Player.get_move``
+src/tic_tac_toe/players.py:6-9) and ships random / minimax / policy-net players behind it, but no
+MCTS.  ``MCTSPlayer`` / ``TicTacToeMCTSPlayer`` fill that hole and plug into the reference's game
+managers unchanged (``ReversiTerminal(p1, p2).play()`` reversi_terminal.py:10-38,
+``TicTacToeHeadless(p1, p2).play()`` tic_tac_toe.py:6-34).  Conventions kept from the reference:
+Reversi players hold ``self.symbol`` in {+1, -1} (reversi_players.py:27-28) and return
+``(None, None)`` when there is no move (:32); the move is the most visited action with the lowest
+row-major index on ties (the argmax-over-legal pick of players.py:92-98).
+
+A single ``get_move`` searches ONE tree -- that is the compatibility boundary, not the fast path;
+throughput comes from ``betazero_b200.selfplay.BatchedSelfPlay`` (thousands of trees per launch).
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import env, mcts
+from .boards import _grid_to_bits
+
+
+class ReversiPlayer(ABC):
+    """reversi_players.py:5-8"""
+
+    @abstractmethod
+    def get_move(self, board):
+        pass
+
+
+class Player(ABC):
+    """src/tic_tac_toe/players.py:6-9"""
+
+    @abstractmethod
+    def get_move(self, board):
+        pass
+
+
+def _make_evaluator(evaluator, net, salt):
+    if evaluator is not None:
+        return evaluator
+    if net is not None:
+        return mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
+    return mcts.HashEvaluator(salt)
+
+
+class MCTSPlayer(ReversiPlayer):
+    """AlphaZero-style MCTS player for Reversi (sizes 4, 6, 8).
+
+    ``net``: a policy/value module from ``betazero_b200.net`` (or pass ``evaluator``); with neither,
+    the deterministic hash pseudo-net is used (parity / tests)."""
+
+    def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, size: int = 8, evaluator=None,
+                 salt: int = 0):
+        self.symbol = symbol  # 1 for X, -1 for O
+        self.n_sims, self.size = int(n_sims), int(size)
+        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_REVERSI, board_size=size, c_puct=c_puct)
+        self.search = mcts.BatchedMCTS(self.pools, _make_evaluator(evaluator, net, salt), use_graph=False)
+        self.last_counts = None
+        self.last_policy = None
+
+    def get_move(self, board):
+        if int(board.size) != self.size:
+            raise ValueError(f"this player was built for {self.size}x{self.size} boards")
+        me, opp = _grid_to_bits(np.asarray(board.board), self.symbol, 8)
+        cnt, pi, _ = self.search.search(env.to_device_u64(np.array([me], np.uint64)),
+                                        env.to_device_u64(np.array([opp], np.uint64)), self.n_sims)
+        a = int(self.search.best_action()[0].item())
+        self.last_counts = cnt[0].cpu().numpy().copy()
+        self.last_policy = pi[0].cpu().numpy().copy()
+        if a >= 64:  # pass (64) or finished game (255): the reference convention for "no moves"
+            return None, None
+        return a >> 3, a & 7
+
+
+class TicTacToeMCTSPlayer(Player):
+    """MCTS player for the reference's tic-tac-toe loop (BASELINE config 1)."""
+
+    def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, evaluator=None, salt: int = 0):
+        self.symbol = symbol
+        self.n_sims = int(n_sims)
+        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_TTT, c_puct=c_puct)
+        self.search = mcts.BatchedMCTS(self.pools, _make_evaluator(evaluator, net, salt), use_graph=False)
+        self.last_counts = None
+        self.last_policy = None
+
+    def get_move(self, board):
+        me, opp = _grid_to_bits(np.asarray(board.board), self.symbol, 3)
+        cnt, pi, _ = self.search.search(env.to_device_u64(np.array([me], np.uint64)),
+                                        env.to_device_u64(np.array([opp], np.uint64)), self.n_sims)
+        a = int(self.search.best_action()[0].item())
+        self.last_counts = cnt[0].cpu().numpy().copy()
+        self.last_policy = pi[0].cpu().numpy().copy()
+        if a >= 9:
+            return None, None
+        return a // 3, a % 3
+
+
+class GreedyNetPlayer(ReversiPlayer):
+    """The reference's AIPlayer.get_move (players.py:84-98) for Reversi: canonicalise with
+    ``symbol * board`` (:85), run the net once, take the best LEGAL move (first maximum in
+    row-major order).  Input goes through the K6 plane kernel, legality through K1."""
+
+    def __init__(self, symbol, net, size: int = 8):
+        self.symbol, self.net, self.size = symbol, net, int(size)
+
+    @torch.no_grad()
+    def get_move(self, board):
+        me_i, opp_i = _grid_to_bits(np.asarray(board.board), self.symbol, 8)
+        me = env.to_device_u64(np.array([me_i], np.uint64))
+        opp = env.to_device_u64(np.array([opp_i], np.uint64))
+        mask = int(env.to_host_u64(env.legal_mask(me, opp, self.size))[0])
+        if mask == 0:
+            return None, None
+        logits, _ = self.net(env.planes(me, opp))
+        logits = logits[0, :64].float().cpu().numpy()
+        legal = np.array([(mask >> a) & 1 for a in range(64)], dtype=bool)
+        a = int(np.argmax(np.where(legal, logits, -np.inf)))
+        return a >> 3, a & 7

@@ -1,0 +1,72 @@
+"""Training step on self-play records ("next" rows 1-2 of SURVEY.md section 8f).
+
+Mirrors the reference's supervised loop where it has one (Adam + cross-entropy, batch 128, lr 1e-4:
+src/tic_tac_toe/SL/train.py:85-113,182-192; 8-fold dihedral augmentation :27-36; model file
+saved at the end :204-214) but with AlphaZero targets: the policy head is fitted to the MCTS visit
+distribution pi (soft-label cross-entropy) and the value head to the game result z.
+The forward/backward is plain PyTorch (the net is library code); the data path -- bitboards to
+planes (K6) and the symmetry augmentation -- runs through the CUDA library.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, env
+
+N_ACTIONS = 65
+
+
+def augment(me: torch.Tensor, opp: torch.Tensor, pi: torch.Tensor, sym: torch.Tensor, size: int = 8):
+    """Apply dihedral transform ``sym[i]`` (0..7, train.py:27-36) to every (board, pi) record."""
+    n = me.numel()
+    me_o, opp_o, pi_o = torch.empty_like(me), torch.empty_like(opp), torch.empty_like(pi)
+    L = _lib.load()
+    _lib.check(L.bz_reversi_symmetry(_lib.dptr(me), _lib.dptr(opp), _lib.dptr(pi.contiguous()), _lib.dptr(sym),
+                                     _lib.dptr(me_o), _lib.dptr(opp_o), _lib.dptr(pi_o), n, size, _lib.stream_ptr()),
+               "bz_reversi_symmetry")
+    return me_o, opp_o, pi_o
+
+
+def make_batch(replay: dict, idx: torch.Tensor, size: int = 8, augment_seed: int | None = None):
+    """(planes bf16 [b,2,8,8], pi f32 [b,65], z f32 [b]) for the records ``idx`` of a replay dict."""
+    me, opp = replay["me"][idx].contiguous(), replay["opp"][idx].contiguous()
+    pi = replay["pi"][idx].contiguous()
+    if augment_seed is not None:
+        g = torch.Generator(device=me.device).manual_seed(int(augment_seed))
+        sym = torch.randint(0, 8, (me.numel(),), dtype=torch.uint8, device=me.device, generator=g)
+        me, opp, pi = augment(me, opp, pi, sym, size)
+    return env.planes(me, opp), pi, replay["z"][idx].float()
+
+
+def loss_fn(net: torch.nn.Module, planes: torch.Tensor, pi: torch.Tensor, z: torch.Tensor):
+    logits, value = net(planes)
+    policy_loss = -(pi * F.log_softmax(logits.float(), dim=-1)).sum(-1).mean()
+    value_loss = F.mse_loss(value.float(), z)
+    return policy_loss + value_loss, policy_loss.detach(), value_loss.detach()
+
+
+def train_step(net: torch.nn.Module, opt: torch.optim.Optimizer, planes, pi, z) -> dict:
+    net.train()
+    opt.zero_grad(set_to_none=True)
+    loss, pl, vl = loss_fn(net, planes, pi, z)
+    loss.backward()
+    opt.step()
+    net.eval()
+    return {"loss": float(loss.detach()), "policy_loss": float(pl), "value_loss": float(vl)}
+
+
+def save_checkpoint(path: str, net: torch.nn.Module, opt: torch.optim.Optimizer | None = None, iteration: int = 0,
+                    extra: dict | None = None) -> None:
+    """state_dict checkpoint (loads with weights_only=True), unlike the reference's whole-module
+    pickle (train.py:204-214) which torch >= 2.6 refuses to load by default."""
+    torch.save({"model": net.state_dict(), "optimizer": opt.state_dict() if opt is not None else None,
+                "iteration": int(iteration), "extra": extra or {}}, path)
+
+
+def load_checkpoint(path: str, net: torch.nn.Module, opt: torch.optim.Optimizer | None = None) -> int:
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    net.load_state_dict(ck["model"])
+    if opt is not None and ck.get("optimizer") is not None:
+        opt.load_state_dict(ck["optimizer"])
+    return int(ck.get("iteration", 0))

@@ -279,6 +279,16 @@ int bz_selfplay_advance(const bz_selfplay_state *st, const bz_tree_pools *pools,
 int bz_philox_u32(uint64_t seed, const int64_t *game_id, const int32_t *ply, uint32_t *out, int64_t n,
                   bz_stream_t stream);
 
+/* Replay augmentation ("next" row 1 of SURVEY.md section 8f): the 8 dihedral transforms of the
+ * reference's dataset expansion (src/tic_tac_toe/SL/train.py:27-36) applied to (board, pi)
+ * records: sym[i] in 0..7 = identity, flip rows, flip columns, rot90 x1, x2, x3 (counter-clockwise,
+ * torch.rot90), transpose, anti-transpose (the reference's 8th lambda, flip(0).t(), duplicates
+ * rot90 x3 and is removed by its dedup; the intended "other diagonal" is used here).  pi: float32
+ * [n, 65], the pass entry is invariant.  size in {4, 6, 8}. */
+int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi, const uint8_t *sym,
+                        uint64_t *me_out, uint64_t *opp_out, float *pi_out, int64_t n, int size,
+                        bz_stream_t stream);
+
 /* INT32 issue-rate microbenchmark (LOP3 / SHF / IADD3 mix) for the env roofline denominator:
  * every thread runs `iters` rounds of 64 dependent-chain-free integer instructions x 4 chains.
  * sink: device uint32 [1].  Returns the number of integer instructions per thread in *ops_per_thread

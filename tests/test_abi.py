@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads and exports every symbol include/betazero_b200.h declares; the
+ctypes mirror structs have the layout of the C structs.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "betazero_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|const char \*)\s*(bz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from betazero_b200 import _lib
+
+    names = _declared_functions()
+    assert len(names) >= 20
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert lib.bz_abi_version() == 1
+    assert lib.bz_error_string(0) == b"ok" and b"argument" in lib.bz_error_string(-1)
+
+
+def test_no_unexpected_dependencies():
+    """the boundary is a plain C ABI: no libtorch / libpython in the link line"""
+    from betazero_b200 import _lib
+
+    out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libpython" not in out and "libc10" not in out
+
+
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """compile a tiny C program against the header and compare sizeof/offsetof with ctypes"""
+    from betazero_b200._lib import BzSelfplayState, BzTreePools
+
+    fields_p = [n for n, _ in BzTreePools._fields_]
+    fields_s = [n for n, _ in BzSelfplayState._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
+            'printf("%zu\\n", sizeof(bz_tree_pools));']
+    prog += [f'printf("%zu\\n", offsetof(bz_tree_pools, {f}));' for f in fields_p]
+    prog += ['printf("%zu\\n", sizeof(bz_selfplay_state));']
+    prog += [f'printf("%zu\\n", offsetof(bz_selfplay_state, {f}));' for f in fields_s]
+    prog += ["return 0;}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    exp = [C.sizeof(BzTreePools)] + [getattr(BzTreePools, f).offset for f in fields_p]
+    exp += [C.sizeof(BzSelfplayState)] + [getattr(BzSelfplayState, f).offset for f in fields_s]
+    assert vals == exp
+
+
+def test_compute_path_refuses_cpu_tensors():
+    """there is no CPU fallback: handing the engine a host tensor is an error, not a slow path"""
+    import torch
+
+    from betazero_b200 import _lib
+
+    with pytest.raises(_lib.BzError, match="CUDA tensor"):
+        _lib.dptr(torch.zeros(4, dtype=torch.int64))
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under betazero_b200/ may import, load or link it"""
+    pkg = os.path.join(ROOT, "betazero_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            txt = open(os.path.join(dirpath, f)).read()
+            assert "liboracle" not in txt and "pyoracle" not in txt, f"{f} references the oracle library"
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+            assert not re.search(r"#include\s+[\"<].*oracle", txt), f"{f} includes oracle code"

@@ -241,7 +241,11 @@ def test_logits_mode_fused_softmax_and_tanh():
     N, W, P = (x.cpu().numpy() for x in s.root_edges())
     logits = ev.out.float().cpu().numpy()
     mask = po.legal_mask(me_h, opp_h)
+    over = po.terminal(me_h, opp_h)[0]
     for i in range(B):
+        if over[i]:  # finished game: nothing is expanded
+            assert N[i].sum() == 0 and P[i].sum() == 0
+            continue
         legal = [a for a in range(64) if (int(mask[i]) >> a) & 1] or [64]
         l = logits[i, legal].astype(np.float64)
         p = np.exp(l - l.max())
