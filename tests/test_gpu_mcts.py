@@ -274,6 +274,8 @@ def test_fused_net_evaluator_agrees_with_parity_evaluator():
         _, _, P = s.root_edges()
         res.append((cnt.cpu().numpy(), P.cpu().numpy()))
     np.testing.assert_allclose(res[0][1], res[1][1], atol=2e-2)
-    assert (res[0][0].sum(1) == n_sims - 1).all() and (res[1][0].sum(1) == n_sims - 1).all()
-    same = (res[0][0].argmax(1) == res[1][0].argmax(1)).mean()
+    live = po.terminal(me_h, opp_h)[0] == 0  # finished games have nothing to search
+    assert (res[0][0].sum(1)[live] == n_sims - 1).all() and (res[1][0].sum(1)[live] == n_sims - 1).all()
+    assert (res[0][0].sum(1)[~live] == 0).all()
+    same = (res[0][0].argmax(1) == res[1][0].argmax(1))[live].mean()
     assert same > 0.8
