@@ -111,6 +111,7 @@ def cpu_selfplay_sample(n_trees: int, n_sims: int, net_kind: str, hidden: int, b
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    po.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
     net = netmod.make_net(net_kind, hidden=hidden, seed=0, device="cpu", dtype=torch.float32)
     me, opp = po.playout_boards(n_trees, seed=42)
     forest = po.OracleForest(n_trees)
@@ -252,6 +253,9 @@ def run_b200(args):
     n_probe = min(S - 1, 400)
     for i in range(n_probe):
         sp.mcts.evaluate()
+        # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
+        # (eager launches are CPU-bound; without this the interval would include a launch gap)
+        torch.cuda._sleep(60_000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         sp.mcts.step()

@@ -365,6 +365,11 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host core."""
+    lib().orc_set_num_threads(int(n))
+
+
 class OracleForest:
     """Many C trees stepped in lockstep (OpenMP over trees): the CPU baseline's counterpart of the
     GPU's BatchedMCTS, usable with any evaluator (e.g. the same PyTorch net on the CPU)."""
