@@ -204,26 +204,60 @@ __global__ void __launch_bounds__(kThreads) ttt_terminal_kernel(const uint16_t *
 }
 
 // INT32 issue-rate microbenchmark ----------------------------------------------------------------
-// 8 independent chains of {SHF, LOP3, IADD3}: the instruction mix of the bitboard kernels.
-__global__ void __launch_bounds__(kThreads) int32_bench_kernel(uint32_t *sink, int iters) {
-    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+// variant 0: 8 independent chains of {SHF, LOP3}: everything on the ALU pipe (the instruction mix
+//            the compiler produces for 64-bit shifts/masks).
+// variant 1: the same 64-bit shift+mask work with the shifts expressed as multiplications by a
+//            run-time power of two (IMAD.WIDE + IMAD on the FMA pipe) and the masks as LOP3 on the
+//            ALU pipe: measures whether the two pipes really issue side by side.
+__device__ __forceinline__ uint64_t shl64_fma(uint64_t x, uint32_t pw) {  // x << log2(pw), pw = 2^s
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32), rlo, rhi;
+    asm("{ .reg .u64 t; .reg .u32 c; mul.wide.u32 t, %2, %4; mov.b64 {%0, c}, t; mad.lo.u32 %1, %3, %4, c; }"
+        : "=r"(rlo), "=r"(rhi) : "r"(lo), "r"(hi), "r"(pw));
+    return ((uint64_t)rhi << 32) | rlo;
+}
+__device__ __forceinline__ uint64_t shr64_fma(uint64_t x, uint32_t pwc) {  // x >> s, pwc = 2^(32-s)
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32), rhi, rlo;
+    asm("{ .reg .u64 t; .reg .u32 c; mul.wide.u32 t, %3, %4; mov.b64 {c, %0}, t; mad.hi.u32 %1, %2, %4, c; }"
+        : "=r"(rhi), "=r"(rlo) : "r"(lo), "r"(hi), "r"(pwc));
+    return ((uint64_t)rhi << 32) | rlo;
+}
+
+__global__ void __launch_bounds__(kThreads) int32_bench_kernel(uint32_t *sink, int iters, int variant, uint32_t pw, uint32_t pwc) {
     const uint32_t k = blockIdx.x | 1u;
+    if (variant == 0) {
+        uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
 #pragma unroll 1
-    for (int it = 0; it < iters; ++it) {
+        for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = __funnelshift_l(a0, a1, 7) ^ (a0 & k);
-            a1 = __funnelshift_l(a1, a2, 9) ^ (a1 | k);
-            a2 = __funnelshift_l(a2, a3, 11) ^ (a2 & k);
-            a3 = __funnelshift_l(a3, a4, 13) ^ (a3 | k);
-            a4 = __funnelshift_l(a4, a5, 3) ^ (a4 & k);
-            a5 = __funnelshift_l(a5, a6, 5) ^ (a5 | k);
-            a6 = __funnelshift_l(a6, a7, 17) ^ (a6 & k);
-            a7 = __funnelshift_l(a7, a0, 19) ^ (a7 | k);
+            for (int u = 0; u < 8; ++u) {
+                a0 = __funnelshift_l(a0, a1, 7) ^ (a0 & k);
+                a1 = __funnelshift_l(a1, a2, 9) ^ (a1 | k);
+                a2 = __funnelshift_l(a2, a3, 11) ^ (a2 & k);
+                a3 = __funnelshift_l(a3, a4, 13) ^ (a3 | k);
+                a4 = __funnelshift_l(a4, a5, 3) ^ (a4 & k);
+                a5 = __funnelshift_l(a5, a6, 5) ^ (a5 | k);
+                a6 = __funnelshift_l(a6, a7, 17) ^ (a6 & k);
+                a7 = __funnelshift_l(a7, a0, 19) ^ (a7 | k);
+            }
         }
+        const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+        if (r == 0xDEADBEEFu) *sink = r;  // keeps the chains live without memory traffic
+    } else {
+        const uint64_t m = 0x7E7E7E7E7E7E7E7EULL ^ k;
+        uint64_t b0 = threadIdx.x * 0x9E3779B97F4A7C15ULL, b1 = b0 ^ 0x1234567ULL, b2 = b0 + 77, b3 = ~b0;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {  // per step and chain: 2 IMAD-class + 2 LOP3
+                b0 = b0 ^ (m & shl64_fma(b0, pw));
+                b1 = b1 ^ (m & shr64_fma(b1, pwc));
+                b2 = b2 ^ (m & shl64_fma(b2, pw));
+                b3 = b3 ^ (m & shr64_fma(b3, pwc));
+            }
+        }
+        const uint64_t r = b0 ^ b1 ^ b2 ^ b3;
+        if (r == 0xDEADBEEFULL) *sink = (uint32_t)r;
     }
-    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-    if (r == 0xDEADBEEFu) *sink = r;  // keeps the chains live without memory traffic
 }
 
 bool size_ok(int size) { return size == 4 || size == 6 || size == 8; }
@@ -332,12 +366,14 @@ int bz_ttt_terminal(const uint16_t *x, const uint16_t *o, uint8_t *over, int8_t 
     return launch_rc();
 }
 
-int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int64_t *ops_per_thread,
+int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int variant, int64_t *ops_per_thread,
                         bz_stream_t stream) {
-    if (!sink || blocks <= 0 || threads <= 0 || threads > kThreads || iters <= 0) return BZ_ERR_ARG;
+    if (!sink || variant < 0 || variant > 1 || blocks <= 0 || threads <= 0 || threads > kThreads || iters <= 0) return BZ_ERR_ARG;
     // per unrolled step: 8 x (SHF + LOP3); the xor/and (or xor/or) pair folds into one LOP3
-    if (ops_per_thread) *ops_per_thread = (int64_t)iters * 8 * 8 * 2;
-    int32_bench_kernel<<<blocks, threads, 0, as_stream(stream)>>>(sink, iters);
+    // variant 0: per unrolled step 8 x (SHF + LOP3) (the xor/and pair folds into one LOP3);
+    // variant 1: per unrolled step 4 x (2 IMAD-class + 2 LOP3)
+    if (ops_per_thread) *ops_per_thread = (int64_t)iters * 8 * (variant == 0 ? 16 : 16);
+    int32_bench_kernel<<<blocks, threads, 0, as_stream(stream)>>>(sink, iters, variant, 1u << 7, 1u << (32 - 9));
     return launch_rc();
 }
 

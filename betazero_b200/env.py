@@ -158,7 +158,7 @@ def ttt_terminal(x: torch.Tensor, o: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------- misc
-def int32_microbench(blocks: int = 148 * 8, threads: int = 256, iters: int = 4096):
+def int32_microbench(blocks: int = 148 * 8, threads: int = 256, iters: int = 4096, variant: int = 0):
     """Runs the LOP3/SHF issue-rate microbenchmark once; returns integer instructions executed
     (per-thread count x threads).  Time it with CUDA events around the call."""
     import ctypes as C
@@ -166,6 +166,6 @@ def int32_microbench(blocks: int = 148 * 8, threads: int = 256, iters: int = 409
     sink = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops = C.c_int64(0)
     L = _lib.load()
-    _lib.check(L.bz_int32_microbench(_lib.dptr(sink), blocks, threads, iters, C.byref(ops), _lib.stream_ptr()),
+    _lib.check(L.bz_int32_microbench(_lib.dptr(sink), blocks, threads, iters, variant, C.byref(ops), _lib.stream_ptr()),
                "bz_int32_microbench")
     return ops.value * blocks * threads

@@ -289,11 +289,11 @@ int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi
                         uint64_t *me_out, uint64_t *opp_out, float *pi_out, int64_t n, int size,
                         bz_stream_t stream);
 
-/* INT32 issue-rate microbenchmark (LOP3 / SHF / IADD3 mix) for the env roofline denominator:
- * every thread runs `iters` rounds of 64 dependent-chain-free integer instructions x 4 chains.
- * sink: device uint32 [1].  Returns the number of integer instructions per thread in *ops_per_thread
- * (host pointer). */
-int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int64_t *ops_per_thread,
+/* INT32 issue-rate microbenchmark for the env roofline denominators.
+ * variant 0: SHF + LOP3 chains, all on the ALU pipe (how 64-bit shifts/masks normally compile);
+ * variant 1: the same 64-bit shift+mask work with shifts as IMAD (FMA pipe) and masks as LOP3 (ALU pipe).
+ * sink: device uint32 [1].  *ops_per_thread (host) receives the integer instructions per thread. */
+int bz_int32_microbench(uint32_t *sink, int blocks, int threads, int iters, int variant, int64_t *ops_per_thread,
                         bz_stream_t stream);
 
 #ifdef __cplusplus

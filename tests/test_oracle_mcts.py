@@ -126,3 +126,29 @@ def test_definition_on_live_reference_matches_c(golden_mcts):
     cnt, W, P, _ = _c_search(me, opp, 120, 9, po.GAME_REVERSI, 8, 1.25)
     c0, w0, p0 = m.root_stats()
     assert np.array_equal(cnt[0], c0) and np.array_equal(W[0], w0) and np.array_equal(P[0], p0)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="live reference not present")
+@pytest.mark.parametrize("n_sims", [25])
+def test_reference_headless_loop_accepts_mcts_players(golden_mcts, n_sims):
+    """BASELINE config 1 with the reference's OWN loop (TicTacToeHeadless.play, tic_tac_toe.py:13-34)
+    and board class: an MCTS player with the reference's get_move interface reproduces the golden
+    visit counts ply by ply (the GPU player does the same on the GPU box, tests/test_gpu_dropin.py)."""
+    from helpers import OracleMCTSPlayer
+
+    Headless = ref_shim.ttt_headless_cls()
+    g = golden_mcts
+    salt = 1
+    counts = []
+
+    class Rec(OracleMCTSPlayer):
+        def get_move(self, board):
+            mv = super().get_move(board)
+            counts.append(self.last_counts.copy())
+            return mv
+
+    game = Headless(Rec(1, n_sims, game="ttt", salt=salt), Rec(-1, n_sims, game="ttt", salt=salt))
+    positions, winner = game.play()
+    p = f"ttt_game_s{n_sims}_k{salt}"
+    assert np.array_equal(np.stack(counts), g[p + "_counts"]) and winner == int(g[p + "_winner"])
+    assert len(positions) == len(counts) + 1
