@@ -83,15 +83,17 @@ def test_arena_follows_reference_loop(size):
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="live reference not present")
-def test_arena_result_equals_reference_terminal_loop(capsys):
+def test_arena_result_equals_reference_terminal_loop(capsys, monkeypatch):
     """the same two players through the reference's own ReversiTerminal.play"""
     import importlib.util
     import sys
 
     RB = ref_shim.reversi_board_cls()
     w, counts, _ = arena.play_game(RB, _First(1), _Last(-1), 6)
-    sys.modules.setdefault("players", type(sys)("players"))
-    sys.modules["players.reversi_players"] = ref_shim.reversi_players_mod()
+    # reversi_terminal.py:8 does `from players.reversi_players import ...`; provide exactly that name
+    # for the duration of this test only (src/tic_tac_toe/players.py is a different `players`)
+    monkeypatch.setitem(sys.modules, "players", type(sys)("players"))
+    monkeypatch.setitem(sys.modules, "players.reversi_players", ref_shim.reversi_players_mod())
     spec = importlib.util.spec_from_file_location(
         "ref_reversi_terminal", ref_shim.REF_ROOT + "/src/reversi/game_logic/reversi_terminal.py")
     mod = importlib.util.module_from_spec(spec)
