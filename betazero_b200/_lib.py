@@ -22,7 +22,7 @@ class BzTreePools(C.Structure):
     _fields_ = [
         ("game", C.c_int32), ("board_size", C.c_int32), ("n_trees", C.c_int32), ("n_actions", C.c_int32),
         ("arena_units", C.c_int32), ("max_depth", C.c_int32), ("c_puct", C.c_float), ("prior_mode", C.c_int32),
-        ("eval_stride", C.c_int32), ("reserved", C.c_int32),
+        ("eval_stride", C.c_int32), ("group_lanes", C.c_int32),
         ("root_me", ptr), ("root_opp", ptr), ("root_meta", ptr), ("arena_used", ptr), ("edge_count", ptr),
         ("sim_count", ptr), ("depth_sum", ptr), ("error", ptr),
         ("arena", ptr),
@@ -92,9 +92,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("BETAZERO_B200_LIB") or _build.LIB  # override: kernel-variant experiments
     try:
-        if _build.needs_build():
+        if path == _build.LIB and _build.needs_build():
             _build.build()
     except Exception as e:  # nvcc missing on a box that received a prebuilt .so is fine
         if not os.path.exists(path):

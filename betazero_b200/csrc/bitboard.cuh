@@ -115,15 +115,15 @@ __device__ __forceinline__ void apply_legal(uint64_t &me, uint64_t &opp, unsigne
     }
 }
 
-// ---- warp-cooperative forms (tree kernels: one warp owns one board) ----------------------------
-// The 8 ray directions are spread over 8 lanes instead of being computed serially by every lane:
-// lane d handles shift {1,7,8,9}[d & 3]; lanes 4..7 work on the bit-reversed board, where the
-// ">>" senses become "<<", so all lanes run the same left-shift code with a per-lane shift count.
-// Results are combined with redux.sync OR.  ~10x fewer issued instructions per warp than the
-// per-thread forms above.
-__device__ __forceinline__ uint64_t warp_or64(unsigned members, uint64_t v) {
-    const unsigned lo = __reduce_or_sync(members, (unsigned)v);
-    const unsigned hi = __reduce_or_sync(members, (unsigned)(v >> 32));
+// ---- group-cooperative forms (tree kernels: a group of G lanes owns one board) -------------------
+// The 8 ray directions are spread over 8 lanes of the group instead of being computed serially by
+// every lane: group lane d handles shift {1,7,8,9}[d & 3]; lanes 4..7 work on the bit-reversed
+// board, where the ">>" senses become "<<", so all lanes run the same left-shift code with a
+// per-lane shift count.  Results are combined with redux.sync OR over the group's lanes.
+// G in {8, 16, 32}; gmask = the group's lanes, gl = lane index inside the group.
+__device__ __forceinline__ uint64_t group_or64(unsigned gmask, uint64_t v) {
+    const unsigned lo = __reduce_or_sync(gmask, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(gmask, (unsigned)(v >> 32));
     return ((uint64_t)hi << 32) | lo;
 }
 
@@ -137,39 +137,51 @@ __device__ __forceinline__ uint64_t fill_left(uint64_t gen, uint64_t pro, int s)
     return f;
 }
 
-__device__ __forceinline__ int lane_shift(int lane) {
-    const int k = lane & 3;  // 1, 7, 8, 9
+__device__ __forceinline__ int lane_shift(int gl) {
+    const int k = gl & 3;  // 1, 7, 8, 9
     return k == 0 ? 1 : 6 + k;
 }
 
-// discs flipped by the move on single-bit board x; every lane returns the full flip set
-__device__ __forceinline__ uint64_t warp_flips(uint64_t x, uint64_t me, uint64_t opp, int lane) {
-    const int s = lane_shift(lane);
-    const bool rev = lane & 4;
+// discs flipped by the move on single-bit board x; every lane of the group returns the full set
+__device__ __forceinline__ uint64_t group_flips(unsigned gmask, int gl, uint64_t x, uint64_t me, uint64_t opp) {
+    const int s = lane_shift(gl);
+    const bool rev = gl & 4;
     uint64_t g = x, m = me, o = opp;
     if (rev) { g = __brevll(g); m = __brevll(m); o = __brevll(o); }
     const uint64_t pro = (s == 8) ? o : (o & kNotEdgeCols);
     uint64_t f = fill_left(g, pro, s);
     f = (m & (f << s)) ? f : 0ULL;  // the run must end on a mover disc (reversi_board.py:56)
     if (rev) f = __brevll(f);
-    if (lane >= 8) f = 0ULL;
-    return warp_or64(0xFFFFFFFFu, f);
+    if (gl >= 8) f = 0ULL;
+    return group_or64(gmask, f);
 }
 
-// legal cells of the mover (me) and of the opponent, computed together: lanes 0..7 mover,
-// lanes 8..15 opponent; every lane returns both masks
-__device__ __forceinline__ void warp_legal_masks(uint64_t me, uint64_t opp, uint64_t cells, int lane,
-                                                 uint64_t &mask_me, uint64_t &mask_opp) {
-    const int s = lane_shift(lane);
-    const bool rev = lane & 4, second = lane & 8;
-    uint64_t g = second ? opp : me, o = second ? me : opp;
-    if (rev) { g = __brevll(g); o = __brevll(o); }
+// candidate moves (before the empty-cell mask) of `gen` against `pro` in direction lane gl & 7
+__device__ __forceinline__ uint64_t dir_moves(int gl, uint64_t gen, uint64_t o) {
+    const int s = lane_shift(gl);
+    const bool rev = gl & 4;
+    if (rev) { gen = __brevll(gen); o = __brevll(o); }
     const uint64_t pro = (s == 8) ? o : (o & kNotEdgeCols);
-    uint64_t mv = fill_left(g, pro, s) << s;
+    uint64_t mv = fill_left(gen, pro, s) << s;
     if (rev) mv = __brevll(mv);
+    return mv;
+}
+
+// legal cells of the mover (me) and of the opponent; every lane of the group returns both masks.
+// G >= 16: lanes 0..7 mover, 8..15 opponent, one pass.  G == 8: two passes over the same 8 lanes.
+template <int G>
+__device__ __forceinline__ void group_legal_masks(unsigned gmask, int gl, uint64_t me, uint64_t opp, uint64_t cells,
+                                                  uint64_t &mask_me, uint64_t &mask_opp) {
     const uint64_t empty = ~(me | opp) & cells;
-    mask_me = warp_or64(0xFFFFFFFFu, (lane < 8) ? mv : 0ULL) & empty;
-    mask_opp = warp_or64(0xFFFFFFFFu, (lane >= 8 && lane < 16) ? mv : 0ULL) & empty;
+    if (G >= 16) {
+        const bool second = gl & 8;
+        const uint64_t mv = dir_moves(gl, second ? opp : me, second ? me : opp);
+        mask_me = group_or64(gmask, (gl < 8) ? mv : 0ULL) & empty;
+        mask_opp = group_or64(gmask, (gl >= 8 && gl < 16) ? mv : 0ULL) & empty;
+    } else {
+        mask_me = group_or64(gmask, dir_moves(gl, me, opp)) & empty;
+        mask_opp = group_or64(gmask, dir_moves(gl, opp, me)) & empty;
+    }
 }
 
 // ---- tic-tac-toe: 9-bit boards, bit = row*3 + col --------------------------------------------

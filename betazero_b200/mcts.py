@@ -38,7 +38,7 @@ class TreePools:
 
     def __init__(self, n_trees: int, sims_cap: int, game: int = GAME_REVERSI, board_size: int = 8,
                  c_puct: float = 1.25, arena_units: int | None = None, max_depth: int | None = None,
-                 prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, device="cuda"):
+                 prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, group_lanes: int = 0, device="cuda"):
         if game not in (GAME_REVERSI, GAME_TTT):
             raise ValueError("game must be GAME_REVERSI or GAME_TTT")
         self.game, self.board_size = game, (3 if game == GAME_TTT else board_size)
@@ -80,7 +80,10 @@ class TreePools:
         s = BzTreePools()
         s.game, s.board_size, s.n_trees, s.n_actions = game, (self.board_size if game == GAME_REVERSI else 8), self.n_trees, self.n_actions
         s.arena_units, s.max_depth, s.c_puct, s.prior_mode = self.arena_units, self.max_depth, self.c_puct, self.prior_mode
-        s.eval_stride, s.reserved = self.eval_stride, 0
+        if group_lanes not in (0, 8, 32):
+            raise ValueError("group_lanes must be 0 (auto), 8 or 32")
+        self.group_lanes = int(group_lanes)
+        s.eval_stride, s.group_lanes = self.eval_stride, self.group_lanes
         for name, _ in BzTreePools._fields_[BzTreePools.N_SCALARS:]:
             setattr(s, name, getattr(self, name).data_ptr())
         self.c_struct = s
