@@ -14,10 +14,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # north_star: Q values and policy targets within 1e-5 relative
 
 
-def _search(me_h, opp_h, n_sims, salt, game=0, size=8, c_puct=1.25, **kw):
+GROUPS = [32, 8]  # lanes per tree: warp-per-tree (small batches) and 4-trees-per-warp (large batches)
+
+
+def _search(me_h, opp_h, n_sims, salt, game=0, size=8, c_puct=1.25, group_lanes=0, **kw):
     from betazero_b200 import env, mcts
 
-    pools = mcts.TreePools(len(me_h), n_sims, game=game, board_size=size, c_puct=c_puct)
+    pools = mcts.TreePools(len(me_h), n_sims, game=game, board_size=size, c_puct=c_puct, group_lanes=group_lanes)
     s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(salt), **kw)
     cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
     return s, cnt.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy()
@@ -29,11 +32,13 @@ def _root_W_P(s):
     return W.cpu().numpy(), P.cpu().numpy()
 
 
+@pytest.mark.parametrize("group", GROUPS)
 @pytest.mark.parametrize("prefix", ["rev8_playout_s48", "rev8_start_s400", "rev8_pass_s64"])
-def test_reversi_matches_golden(golden_mcts, prefix):
+def test_reversi_matches_golden(golden_mcts, prefix, group):
     g = golden_mcts
     n_sims, salt = (int(v) for v in g[prefix + "_meta"])
-    s, cnt, pi, q = _search(g[prefix + "_me"], g[prefix + "_opp"], n_sims, salt, c_puct=float(g["c_puct"]))
+    s, cnt, pi, q = _search(g[prefix + "_me"], g[prefix + "_opp"], n_sims, salt, c_puct=float(g["c_puct"]),
+                            group_lanes=group)
     assert np.array_equal(cnt, g[prefix + "_counts"])
     W, P = _root_W_P(s)
     assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])
@@ -44,34 +49,38 @@ def test_reversi_matches_golden(golden_mcts, prefix):
     np.testing.assert_allclose(q, exp_q, rtol=RTOL, atol=0)
 
 
+@pytest.mark.parametrize("group", GROUPS)
 @pytest.mark.parametrize("n_sims", [25, 100])
-def test_config1_ttt_selfplay_visit_counts(golden_mcts, n_sims):
+def test_config1_ttt_selfplay_visit_counts(golden_mcts, n_sims, group):
     """BASELINE config 1: tic-tac-toe MCTS self-play, root visit counts of every ply bit-exact"""
     from betazero_b200 import mcts
 
     g = golden_mcts
     for salt in range(4):
         p = f"ttt_game_s{n_sims}_k{salt}"
-        s, cnt, pi, q = _search(g[p + "_me"], g[p + "_opp"], n_sims, salt, game=mcts.GAME_TTT, c_puct=float(g["c_puct"]))
+        s, cnt, pi, q = _search(g[p + "_me"], g[p + "_opp"], n_sims, salt, game=mcts.GAME_TTT, c_puct=float(g["c_puct"]),
+                                group_lanes=group)
         assert np.array_equal(cnt, g[p + "_counts"])
         assert np.array_equal(s.best_action().cpu().numpy(), g[p + "_action"])
 
 
+@pytest.mark.parametrize("group", GROUPS)
 @pytest.mark.parametrize("size,n_sims", [(4, 40), (6, 24)])
-def test_small_boards_match_golden(golden_mcts, size, n_sims):
+def test_small_boards_match_golden(golden_mcts, size, n_sims, group):
     g = golden_mcts
     p = f"rev{size}_game_s{n_sims}"
-    s, cnt, _, _ = _search(g[p + "_me"], g[p + "_opp"], n_sims, 2, size=size, c_puct=float(g["c_puct"]))
+    s, cnt, _, _ = _search(g[p + "_me"], g[p + "_opp"], n_sims, 2, size=size, c_puct=float(g["c_puct"]), group_lanes=group)
     assert np.array_equal(cnt, g[p + "_counts"])
     assert np.array_equal(s.best_action().cpu().numpy(), g[p + "_action"])
 
 
-def test_config3_1024_trees_100_sims_vs_c_oracle():
+@pytest.mark.parametrize("group", GROUPS)
+def test_config3_1024_trees_100_sims_vs_c_oracle(group):
     """BASELINE config 3 shape: 1024 concurrent trees, 100 sims/move (hash evaluator for parity)."""
     from oracle import pyoracle as po
 
     me_h, opp_h = po.playout_boards(1024, seed=5)
-    s, cnt, pi, q = _search(me_h, opp_h, 100, salt=17)
+    s, cnt, pi, q = _search(me_h, opp_h, 100, salt=17, group_lanes=group)
     r_cnt, r_W, r_P, ctr = po.search_hash(me_h, opp_h, 100, po.GAME_REVERSI, 8, 1.25, 17)
     assert np.array_equal(cnt, r_cnt)
     W, P = _root_W_P(s)
@@ -82,14 +91,53 @@ def test_config3_1024_trees_100_sims_vs_c_oracle():
     assert st["edges"] == ctr["edges"]
 
 
-def test_800_sims_vs_c_oracle():
+@pytest.mark.parametrize("group", GROUPS)
+def test_800_sims_vs_c_oracle(group):
     """the headline search length (800 sims/move) on 128 trees, graph + fused path"""
     from oracle import pyoracle as po
 
     me_h, opp_h = po.playout_boards(128, seed=6)
-    s, cnt, _, _ = _search(me_h, opp_h, 800, salt=1)
+    s, cnt, _, _ = _search(me_h, opp_h, 800, salt=1, group_lanes=group)
     r_cnt, _, _, _ = po.search_hash(me_h, opp_h, 800, po.GAME_REVERSI, 8, 1.25, 1)
     assert np.array_equal(cnt, r_cnt)
+
+
+def test_headline_size_4096_trees_800_sims():
+    """BASELINE configs[3] size: 4096 trees x 800 iterations.  The C oracle checks a 160-tree sample
+    bit for bit (trees are independent); invariants are checked on every tree."""
+    from oracle import pyoracle as po
+
+    B, S = 4096, 800
+    me_h, opp_h = po.playout_boards(B, seed=44)
+    s, cnt, pi, q = _search(me_h, opp_h, S, salt=9)
+    live = po.terminal(me_h, opp_h)[0] == 0
+    assert (cnt.sum(1)[live] == S - 1).all() and (cnt.sum(1)[~live] == 0).all()
+    np.testing.assert_allclose(pi.sum(1)[live], 1.0, atol=1e-5)
+    mask = po.legal_mask(me_h, opp_h)
+    legal = ((mask[:, None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    assert (cnt[:, :64][~legal] == 0).all()  # no visits on illegal cells
+    assert ((cnt[:, 64] > 0) == ((mask == 0) & live)).all()  # pass is searched exactly when forced
+    assert (np.abs(q) <= 1.0).all()
+    st = s.stats()
+    assert st["sims"] == int(live.sum()) * S + int((~live).sum()) * S  # finished roots still count iterations
+    sample = np.arange(0, B, B // 160)
+    r_cnt, r_W, r_P, _ = po.search_hash(me_h[sample], opp_h[sample], S, po.GAME_REVERSI, 8, 1.25, 9)
+    assert np.array_equal(cnt[sample], r_cnt)
+    W, P = _root_W_P(s)
+    assert np.array_equal(W[sample], r_W) and np.array_equal(P[sample], r_P)
+
+
+def test_large_batch_uses_eight_lane_groups():
+    """>= 8192 trees: the 4-trees-per-warp kernels are selected automatically; same answers"""
+    from oracle import pyoracle as po
+
+    B, S = 8192 + 5, 60
+    me_h, opp_h = po.playout_boards(512, seed=3)
+    me_h, opp_h = np.resize(me_h, B), np.resize(opp_h, B)
+    s, cnt, _, _ = _search(me_h, opp_h, S, salt=2)
+    r_cnt, _, _, _ = po.search_hash(me_h[:512], opp_h[:512], S, po.GAME_REVERSI, 8, 1.25, 2)
+    assert np.array_equal(cnt[:512], r_cnt)
+    assert np.array_equal(cnt[512:1024], r_cnt) and np.array_equal(cnt[-5:], r_cnt[(B - 5) % 512:][:5])
 
 
 def test_fused_graph_and_plain_paths_agree():
@@ -106,7 +154,8 @@ def test_fused_graph_and_plain_paths_agree():
             assert np.array_equal(cnt, ref[0]) and np.array_equal(pi, ref[1]) and np.array_equal(q, ref[2])
 
 
-def test_lockstep_float_priors_vs_c_oracle():
+@pytest.mark.parametrize("group", GROUPS)
+def test_lockstep_float_priors_vs_c_oracle(group):
     """real-net-like float priors and values: feed the SAME (w, v) to the GPU trees and to the
     oracle trees at every iteration and compare leaves, statuses and final statistics bit for bit"""
     from betazero_b200 import env, mcts
@@ -114,7 +163,7 @@ def test_lockstep_float_priors_vs_c_oracle():
 
     B, n_sims = 96, 150
     me_h, opp_h = po.playout_boards(B, seed=12)
-    pools = mcts.TreePools(B, n_sims, c_puct=2.0)
+    pools = mcts.TreePools(B, n_sims, c_puct=2.0, group_lanes=group)
     s = mcts.BatchedMCTS(pools, None, use_graph=False)
     s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
     trees = [po.OracleTree(po.GAME_REVERSI, 8, 2.0) for _ in range(B)]
@@ -211,7 +260,8 @@ def test_hash_eval_kernel_matches_oracle():
             assert np.array_equal(w[i], rw) and v[i] == rv
 
 
-def test_logits_mode_fused_softmax_and_tanh():
+@pytest.mark.parametrize("group", GROUPS)
+def test_logits_mode_fused_softmax_and_tanh(group):
     """BZ_PRIOR_LOGITS_BF16: the tree kernel does the legal-move softmax and tanh itself.  Floating
     point with fast intrinsics, so tolerance-checked (1e-5 abs on priors) against numpy."""
     from betazero_b200 import env, mcts
@@ -219,7 +269,7 @@ def test_logits_mode_fused_softmax_and_tanh():
 
     B = 512
     me_h, opp_h = po.playout_boards(B, seed=31)
-    pools = mcts.TreePools(B, 4, prior_mode=mcts.PRIOR_LOGITS_BF16, eval_stride=72)
+    pools = mcts.TreePools(B, 4, prior_mode=mcts.PRIOR_LOGITS_BF16, eval_stride=72, group_lanes=group)
 
     class Raw:
         prior_mode = mcts.PRIOR_LOGITS_BF16
