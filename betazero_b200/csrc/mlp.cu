@@ -1,0 +1,263 @@
+// Fused policy/value MLP inference for sm_100a: the whole 128 -> 256 -> 256 -> 256 -> (65 + 1) network of
+// betazero_b200.net.PolicyValueMLP (the reference's TicTacToeNet family, SL/neural_networks.py:4-30, widened)
+// in ONE launch instead of four library GEMMs.  This is the only dense contraction on the self-play path, so
+// it is the only code here that uses the tensor cores: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by
+// one thread, accumulators in TMEM, operands staged in shared memory in the canonical K-major SWIZZLE_128B
+// layout, tcgen05.ld epilogue (bias + ReLU + bf16 round) that writes the next layer's A operand straight back
+// into shared memory.  One CTA owns 128 leaves (rows); the activations never leave the SM between layers.
+//
+// Numerics = the PyTorch bf16 module: bf16 inputs/weights, fp32 accumulate, fp32 bias add, ReLU, round to bf16
+// after every layer.  Output: bf16 [B, 72] = 65 policy logits, the pre-tanh value, zero padding -- exactly the
+// BZ_PRIOR_LOGITS_BF16 input of the tree kernel.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace bz {
+namespace {
+
+constexpr int kRows = 128;       // leaves per CTA == UMMA M
+constexpr int kIn = 128;         // 2 x 8 x 8 canonical planes
+constexpr int kHidden = 256;
+constexpr int kHeadRows = 80;    // 65 logits + value, padded to a legal UMMA N (multiple of 16)
+constexpr int kOutStride = 72;   // row stride of the output (multiple of 8 elements: 16-byte rows)
+constexpr int kThreads = 256;
+constexpr int kSlabA = kRows * 128;      // one 64-element K slab of A: 128 rows x 128 B
+constexpr int kSlabB = kHidden * 128;    // one K slab of B: 256 rows x 128 B
+constexpr int kSmemA = 4 * kSlabA;       // 64 KB
+constexpr int kSmemB = 4 * kSlabB;       // 128 KB
+constexpr int kSmemBias = kHidden * 4;   // 1 KB
+constexpr int kSmemTotal = kSmemA + kSmemB + kSmemBias + 64 + 1024;  // + barrier/tmem slot + alignment slack
+constexpr int kTmemCols = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO = 1 (unused
+// for swizzled K-major), version 1 (sm_100), layout type 2.  See cute/arch/mma_sm100_desc.hpp (CUTLASS).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor for kind::f16: D = F32, A = B = BF16, both K-major, shape M x N
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+    const int bytes = valid ? 16 : 0;  // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+// mbarrier phase wait with a bounded spin: a descriptor bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// rows x K bf16, row-major in global (row stride `ld` elements) -> K-major SWIZZLE_128B slabs in shared memory:
+// 16-byte chunk j of row r in slab s lands at s*slab_bytes + r*128 + ((j ^ (r & 7)) * 16)
+__device__ __forceinline__ void load_operand(uint32_t sbase, int slab_bytes, const __nv_bfloat16 *g, int rows, int K, int ld,
+                                             int valid_rows) {
+    const int chunks_per_row = K / 8;
+    const int total = rows * chunks_per_row;
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
+        const int s = c >> 3, j = c & 7;
+        const uint32_t dst = sbase + s * slab_bytes + r * 128 + ((j ^ (r & 7)) << 4);
+        const bool ok = r < valid_rows;
+        cp_async16(dst, g + (size_t)(ok ? r : 0) * ld + c * 8, ok);
+    }
+}
+
+struct MlpParams {
+    const __nv_bfloat16 *x;                 // [B, 128]
+    const __nv_bfloat16 *w[4], *b[4];       // [256,128] [256,256] [256,256] [80,256]; biases 256/256/256/80
+    __nv_bfloat16 *out;                     // [B, 72]
+    int B;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B operands need 1024-byte alignment
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t sA = base, sB = base + kSmemA;
+    float *sBias = reinterpret_cast<float *>(smem + kSmemA + kSmemB);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kSmemA + kSmemB + kSmemBias);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const uint32_t bar_addr = smem_u32(bar);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kRows;
+    const int valid_rows = min(kRows, p.B - row0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // layer-0 operands: the leaf planes and W1
+    load_operand(sA, kSlabA, p.x + (size_t)row0 * kIn, kRows, kIn, kIn, valid_rows);
+    load_operand(sB, kSlabB, p.w[0], kHidden, kIn, kIn, kHidden);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+#pragma unroll 1
+    for (int layer = 0; layer < 4; ++layer) {
+        const int K = layer == 0 ? kIn : kHidden;
+        const int N = layer == 3 ? kHeadRows : kHidden;
+        if (threadIdx.x == 0) {
+            const uint32_t idesc = umma_idesc(kRows, N);
+            for (int k = 0; k < K / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+                const uint32_t off = (uint32_t)(k >> 2), kk = (uint32_t)(k & 3) * 32u;
+                umma_bf16(tmem, umma_desc(sA + off * kSlabA + kk), umma_desc(sB + off * kSlabB + kk), idesc, k > 0);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+        }
+        // bias of this layer -> shared (overlaps the MMAs)
+        for (int i = threadIdx.x; i < N; i += kThreads) sBias[i] = __bfloat162float(p.b[layer][i]);
+        mbar_wait(bar_addr, (uint32_t)(layer & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncthreads();  // bias visible; A and B are free again (the MMAs have read them)
+        if (layer < 3) {  // next layer's weights stream in while the epilogue runs
+            const int nextN = layer == 2 ? kHeadRows : kHidden;
+            load_operand(sB, kSlabB, p.w[layer + 1], nextN, kHidden, kHidden, nextN);
+        }
+        // epilogue: thread <-> accumulator row; warp w reads TMEM lanes 32*(w%4).., column half w/4
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        if (layer < 3) {
+            const int c_begin = (warp >> 2) * (kHidden / 2);
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_begin + kHidden / 2; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(trow + (uint32_t)c0, acc);
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a = fmaxf(__uint_as_float(acc[2 * j]) + sBias[c0 + 2 * j], 0.f);
+                    const float b = fmaxf(__uint_as_float(acc[2 * j + 1]) + sBias[c0 + 2 * j + 1], 0.f);
+                    packed[j] = pack_bf16(a, b);
+                }
+                // 32 columns = 4 chunks of 16 B in slab c0/64, chunk index (c0%64)/8 + q, swizzled by the row
+                const uint32_t rowbase = sA + (uint32_t)(c0 >> 6) * kSlabA + (uint32_t)r * 128u;
+                const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t dst = rowbase + (uint32_t)(((j0 + q) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * q]), "r"(packed[4 * q + 1]),
+                                 "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                 : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        } else if (warp < 4) {
+            // head: 72 output columns (65 logits, value, padding) -> global, bf16, no activation
+            __nv_bfloat16 *orow = p.out + (size_t)(row0 + r) * kOutStride;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 96; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(trow + (uint32_t)c0, acc);  // columns >= 80 of the last chunk are stale accumulators: never stored
+                if (r < valid_rows) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = c0 + q * 8;
+                        if (c < kOutStride) {
+                            uint4 v;
+                            v.x = pack_bf16(__uint_as_float(acc[q * 8 + 0]) + sBias[c + 0], __uint_as_float(acc[q * 8 + 1]) + sBias[c + 1]);
+                            v.y = pack_bf16(__uint_as_float(acc[q * 8 + 2]) + sBias[c + 2], __uint_as_float(acc[q * 8 + 3]) + sBias[c + 3]);
+                            v.z = pack_bf16(__uint_as_float(acc[q * 8 + 4]) + sBias[c + 4], __uint_as_float(acc[q * 8 + 5]) + sBias[c + 5]);
+                            v.w = pack_bf16(__uint_as_float(acc[q * 8 + 6]) + sBias[c + 6], __uint_as_float(acc[q * 8 + 7]) + sBias[c + 7]);
+                            *reinterpret_cast<uint4 *>(orow + c) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace
+}  // namespace bz
+
+using namespace bz;
+
+extern "C" int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const void *w2, const void *b2, const void *w3,
+                              const void *b3, const void *w_head, const void *b_head, void *out_bf16, int64_t n, int in_features,
+                              int hidden, int head_rows, int out_stride, bz_stream_t stream) {
+    if (n < 0 || in_features != kIn || hidden != kHidden || head_rows != kHeadRows || out_stride != kOutStride) return BZ_ERR_ARG;
+    if (n && (!x_bf16 || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w_head || !b_head || !out_bf16)) return BZ_ERR_ARG;
+    if (!aligned16(x_bf16) || !aligned16(w1) || !aligned16(w2) || !aligned16(w3) || !aligned16(w_head) || !aligned16(out_bf16))
+        return BZ_ERR_UNALIGNED;
+    if (n == 0) return BZ_OK;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        if (e != cudaSuccess) return cuda_rc(e);
+        configured = true;
+    }
+    MlpParams p;
+    p.x = (const __nv_bfloat16 *)x_bf16;
+    p.w[0] = (const __nv_bfloat16 *)w1; p.b[0] = (const __nv_bfloat16 *)b1;
+    p.w[1] = (const __nv_bfloat16 *)w2; p.b[1] = (const __nv_bfloat16 *)b2;
+    p.w[2] = (const __nv_bfloat16 *)w3; p.b[2] = (const __nv_bfloat16 *)b3;
+    p.w[3] = (const __nv_bfloat16 *)w_head; p.b[3] = (const __nv_bfloat16 *)b_head;
+    p.out = (__nv_bfloat16 *)out_bf16;
+    p.B = (int)n;
+    mlp_kernel<<<(unsigned)((n + kRows - 1) / kRows), kThreads, kSmemTotal, as_stream(stream)>>>(p);
+    return launch_rc();
+}

@@ -168,10 +168,11 @@ class FusedNetEvaluator:
 
     prior_mode = PRIOR_LOGITS_BF16
 
-    def __init__(self, net: torch.nn.Module):
+    def __init__(self, net: torch.nn.Module, use_kernel: bool | None = None):
         if not hasattr(net, "forward_raw"):
             raise TypeError("FusedNetEvaluator needs a net with forward_raw()")
         self.net = net
+        self.use_kernel = use_kernel  # None: the single-launch tcgen05 MLP kernel when the shape allows
 
     def bind(self, pools: "TreePools"):
         B = max(pools.n_trees, 1)
@@ -189,7 +190,7 @@ class FusedNetEvaluator:
 
     @torch.no_grad()
     def __call__(self, pools: "TreePools") -> None:
-        self.net.forward_raw(pools.leaf_planes, out=self.out)
+        self.net.forward_raw(pools.leaf_planes, out=self.out, fused=self.use_kernel)
 
 
 class BatchedMCTS:

@@ -40,25 +40,51 @@ class PolicyValueMLP(nn.Module):
         x = self.relu(self.fc3(x))
         return self.policy(x), torch.tanh(self.value(x)).squeeze(-1)
 
-    # -- inference fast path: 4 GEMM launches, bias+ReLU in the cuBLASLt epilogue, one fused head ----
+    # -- inference fast paths -----------------------------------------------------------------------
     @torch.no_grad()
     def prepare_inference(self) -> None:
-        """(Re)build the fused policy+value head [raw_width, H]; call after every weight update."""
-        w = torch.zeros((self.raw_width, self.policy.in_features), dtype=self.policy.weight.dtype,
-                        device=self.policy.weight.device)
-        b = torch.zeros(self.raw_width, dtype=w.dtype, device=w.device)
-        A = self.n_actions
+        """(Re)build the fused policy+value head; call after every weight update."""
+        A, H = self.n_actions, self.policy.in_features
+        rows = max(self.raw_width, 80) if self.raw_width <= 80 else self.raw_width  # 80 = UMMA N of the fused kernel
+        w = torch.zeros((rows, H), dtype=self.policy.weight.dtype, device=self.policy.weight.device)
+        b = torch.zeros(rows, dtype=w.dtype, device=w.device)
         w[:A], w[A] = self.policy.weight, self.value.weight[0]
         b[:A], b[A] = self.policy.bias, self.value.bias[0]
-        self._head = (w, b)
+        self._head_full = (w.contiguous(), b.contiguous())
+        self._head = (w[: self.raw_width], b[: self.raw_width])
         self._w = [m.weight.t() for m in (self.fc1, self.fc2, self.fc3)]
 
+    def fused_kernel_ok(self, planes: torch.Tensor) -> bool:
+        """the hand-written tcgen05 kernel covers exactly the Reversi shape in bf16 on a GPU"""
+        return (planes.is_cuda and planes.dtype == torch.bfloat16 and self.fc1.weight.dtype == torch.bfloat16
+                and self.fc1.in_features == 128 and self.fc1.out_features == 256 and self.raw_width == 72
+                and not self.training)
+
     @torch.no_grad()
-    def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A."""
+    def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None, fused: bool | None = None) -> torch.Tensor:
+        """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A.
+
+        ``fused=None`` picks the single-launch tcgen05 kernel (``bz_mlp_forward``) when the shape
+        allows, else 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch."""
         if self._head is None:
             self.prepare_inference()
-        x = planes.reshape(planes.shape[0], -1)
+        B = planes.shape[0]
+        if fused is None:
+            fused = self.fused_kernel_ok(planes)
+        if fused:
+            from . import _lib
+
+            if out is None:
+                out = torch.empty((B, self.raw_width), dtype=torch.bfloat16, device=planes.device)
+            hw, hb = self._head_full
+            x = planes.reshape(B, -1)
+            L = _lib.load()
+            _lib.check(L.bz_mlp_forward(_lib.dptr(x), _lib.dptr(self.fc1.weight), _lib.dptr(self.fc1.bias),
+                                        _lib.dptr(self.fc2.weight), _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.weight),
+                                        _lib.dptr(self.fc3.bias), _lib.dptr(hw), _lib.dptr(hb), _lib.dptr(out), B,
+                                        128, 256, hw.shape[0], self.raw_width, _lib.stream_ptr()), "bz_mlp_forward")
+            return out
+        x = planes.reshape(B, -1).to(self.fc1.weight.dtype)
         x = torch._addmm_activation(self.fc1.bias, x, self._w[0])
         x = torch._addmm_activation(self.fc2.bias, x, self._w[1])
         x = torch._addmm_activation(self.fc3.bias, x, self._w[2])

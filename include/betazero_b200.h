@@ -289,6 +289,18 @@ int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi
                         uint64_t *me_out, uint64_t *opp_out, float *pi_out, int64_t n, int size,
                         bz_stream_t stream);
 
+/* Fused policy/value MLP inference (the network is the only dense contraction on the path and the
+ * only tensor-core user): x bf16 [n, 128] canonical planes -> 128 -> 256 -> 256 -> 256 (ReLU) ->
+ * head, all four layers in one tcgen05/TMEM kernel.  Architecture = the reference's TicTacToeNet
+ * family (src/tic_tac_toe/SL/neural_networks.py:4-30, hidden 256 per SL/train.py:186) widened to
+ * 8x8 with a value column.  Weights bf16 row-major [out, in] as torch.nn.Linear stores them; the
+ * head is [80, 256] (65 policy rows, 1 value row, zero padding); biases bf16.  out: bf16
+ * [n, 72] = BZ_PRIOR_LOGITS_BF16 input of bz_mcts_step.  Only this shape is supported
+ * (in_features 128, hidden 256, head_rows 80, out_stride 72); anything else returns BZ_ERR_ARG. */
+int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const void *w2, const void *b2,
+                   const void *w3, const void *b3, const void *w_head, const void *b_head, void *out_bf16,
+                   int64_t n, int in_features, int hidden, int head_rows, int out_stride, bz_stream_t stream);
+
 /* INT32 issue-rate microbenchmark for the env roofline denominators.
  * variant 0: SHF + LOP3 chains, all on the ALU pipe (how 64-bit shifts/masks normally compile);
  * variant 1: the same 64-bit shift+mask work with shifts as IMAD (FMA pipe) and masks as LOP3 (ALU pipe).

@@ -1,0 +1,79 @@
+"""GPU: the fused tcgen05 MLP kernel (bz_mlp_forward) against the PyTorch module it replaces.
+Floating point (bf16 inputs, fp32 accumulate, bf16 rounding after every layer), so the comparison
+is tolerance based: the two differ only in fp32 accumulation order."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 3e-2, 3e-2  # bf16 has 8 mantissa bits; logits are O(1)
+
+
+def _planes(B, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randint(0, 3, (B, 64), device="cuda", generator=g)
+    return torch.stack([(a == 1), (a == 2)], dim=1).reshape(B, 2, 8, 8).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B", [1, 7, 128, 129, 1000, 4096])
+def test_fused_mlp_matches_torch_module(B):
+    from betazero_b200 import net
+
+    m = net.make_net("mlp", seed=5)
+    with torch.no_grad():  # larger weights than the default init so every layer matters
+        for prm in m.parameters():
+            prm.mul_(1.7)
+    m.prepare_inference()
+    x = _planes(B, B)
+    assert m.fused_kernel_ok(x)
+    got = m.forward_raw(x, fused=True).float()
+    ref = m.forward_raw(x, fused=False).float()
+    torch.cuda.synchronize()
+    assert got.shape == (B, 72)
+    np.testing.assert_allclose(got[:, :66].cpu().numpy(), ref[:, :66].cpu().numpy(), atol=ATOL, rtol=RTOL)
+    assert (got[:, 66:] == 0).all()  # zero padding columns
+    logits, v = m(x)
+    np.testing.assert_allclose(got[:, :65].cpu().numpy(), logits.float().cpu().numpy(), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(torch.tanh(got[:, 65]).cpu().numpy(), v.float().cpu().numpy(), atol=ATOL)
+    # an fp64 reference on the same bf16 weights bounds both implementations
+    with torch.no_grad():
+        h = x.reshape(B, -1).double()
+        for fc in (m.fc1, m.fc2, m.fc3):
+            h = torch.relu(h @ fc.weight.double().t() + fc.bias.double()).to(torch.bfloat16).double()
+        exact = h @ m.policy.weight.double().t() + m.policy.bias.double()
+    assert (got[:, :65].double() - exact).abs().max().item() < 4e-2
+
+
+def test_fused_mlp_is_deterministic_and_row_independent():
+    from betazero_b200 import net
+
+    m = net.make_net("mlp", seed=1)
+    x = _planes(300, 3)
+    a = m.forward_raw(x, fused=True).clone()
+    b = m.forward_raw(x, fused=True)
+    assert torch.equal(a, b)
+    c = m.forward_raw(x[37:38].contiguous(), fused=True)
+    assert torch.equal(c[0], a[37])  # a row's result does not depend on its batch
+
+
+def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
+    from betazero_b200 import env, mcts, net
+    from oracle import pyoracle as po
+
+    B, n_sims = 256, 48
+    me_h, opp_h = po.playout_boards(B, seed=8)
+    model = net.make_net("mlp", seed=3)
+    res = []
+    for fused in (True, False):
+        ev = mcts.FusedNetEvaluator(model, use_kernel=fused)
+        pools = mcts.TreePools(B, n_sims)
+        s = mcts.BatchedMCTS(pools, ev, use_graph=True, graph_unroll=8)
+        cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
+        _, _, P = s.root_edges()
+        res.append((cnt.cpu().numpy(), P.cpu().numpy()))
+    np.testing.assert_allclose(res[0][1], res[1][1], atol=2e-2)
+    live = po.terminal(me_h, opp_h)[0] == 0
+    assert (res[0][0].sum(1)[live] == n_sims - 1).all()
+    assert (res[0][0].argmax(1) == res[1][0].argmax(1))[live].mean() > 0.8
