@@ -172,7 +172,7 @@ class FusedNetEvaluator:
         if not hasattr(net, "forward_raw"):
             raise TypeError("FusedNetEvaluator needs a net with forward_raw()")
         self.net = net
-        self.use_kernel = use_kernel  # None: the single-launch tcgen05 MLP kernel when the shape allows
+        self.use_kernel = use_kernel  # True: the single-launch tcgen05 MLP kernel (bz_mlp_forward); default library GEMMs
 
     def bind(self, pools: "TreePools"):
         B = max(pools.n_trees, 1)
