@@ -70,6 +70,7 @@ SIGNATURES = {
     "bz_mcts_root_policy": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_root_edges": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_best_action": [_PP, ptr, ptr],
+    "bz_mcts_root_noise": [_PP, ptr, _F, ptr],
     "bz_hash_eval": [ptr, ptr, _U64, _INT, ptr, ptr, _I64, ptr],
     "bz_selfplay_init": [_SP, _I64, ptr],
     "bz_selfplay_advance": [_SP, _PP, ptr, ptr],

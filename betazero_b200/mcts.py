@@ -201,8 +201,12 @@ class BatchedMCTS:
     ``leaf_me/leaf_opp``) and fills them; it is captured into the CUDA graph with the tree kernel.
     """
 
-    def __init__(self, pools: TreePools, evaluator, use_graph: bool = True, graph_unroll: int = 16, fused: bool = True):
+    def __init__(self, pools: TreePools, evaluator, use_graph: bool = True, graph_unroll: int = 16, fused: bool = True,
+                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, noise_seed: int = 0):
         self.pools, self.evaluator = pools, evaluator
+        # root exploration noise (self-play only; 0 = off, which every parity test uses)
+        self.dirichlet_alpha, self.dirichlet_eps = float(dirichlet_alpha), float(dirichlet_eps)
+        self._noise_gen = torch.Generator(device=pools.device).manual_seed(int(noise_seed)) if dirichlet_alpha > 0 else None
         self.use_graph, self.unroll, self.fused = bool(use_graph), int(graph_unroll), bool(fused)
         B, A = max(pools.n_trees, 1), pools.n_actions
         if evaluator is None:
@@ -287,6 +291,13 @@ class BatchedMCTS:
             return
         self.select()
         inner = n_sims - 1
+        if self.dirichlet_alpha > 0 and inner > 0:
+            # iteration 1 expands the root; perturb its priors before the second descent
+            self.evaluate()
+            self.expand_backup()
+            self.add_root_noise()
+            self.select()
+            inner -= 1
         if self.use_graph and inner >= self.unroll:
             if self._graph is None:
                 raise RuntimeError("call prepare() before the first graph search")
@@ -299,6 +310,17 @@ class BatchedMCTS:
             self.step()
         self.evaluate()
         self.expand_backup()
+
+    def add_root_noise(self) -> None:
+        """P_root <- (1 - eps) P + eps Dirichlet(alpha) over the root's legal moves (bz_mcts_root_noise).
+        Gamma(alpha, 1) samples come from torch (plumbing); the kernel normalises over the legal edges."""
+        p = self.pools
+        shape = (max(p.n_trees, 1), p.n_actions)
+        alpha = torch.full(shape, self.dirichlet_alpha, dtype=torch.float32, device=p.device)
+        noise = torch._standard_gamma(alpha, generator=self._noise_gen).clamp_min_(1e-30)
+        _lib.check(self._L.bz_mcts_root_noise(p._ref, _lib.dptr(noise), self.dirichlet_eps, _lib.stream_ptr()),
+                   "bz_mcts_root_noise")
+        self.launches += 1
 
     def prepare(self) -> None:
         """Capture the CUDA graph (clobbers the pending leaf state: call before reset())."""

@@ -210,6 +210,13 @@ int bz_mcts_expand_backup(const bz_tree_pools *pools, const void *eval_out, cons
 /* K7+K5+K6 in one launch: finish iteration i with the evaluator's output, start iteration i+1. */
 int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *value, bz_stream_t stream);
 
+/* Root exploration noise (AlphaZero self-play; OFF in every parity test): for each tree whose
+ * root is expanded, P[e] <- (1 - eps) * P[e] + eps * noise[a_e] / sum over the root's edges of
+ * noise[a].  noise: float32 [n_trees, n_actions] > 0 (e.g. Gamma(alpha, 1) samples: the
+ * normalised vector is then Dirichlet(alpha) over the legal moves).  Call after the iteration that
+ * expanded the root and before the next select. */
+int bz_mcts_root_noise(const bz_tree_pools *pools, const float *noise, float eps, bz_stream_t stream);
+
 /* Read one tree's root edges back in action order (debug / tests): N, W, P scattered by action
  * into rows of n_actions (zeros elsewhere).  Any output may be NULL. */
 int bz_mcts_root_edges(const bz_tree_pools *pools, int32_t *N, float *W, float *P, bz_stream_t stream);

@@ -329,3 +329,50 @@ def test_fused_net_evaluator_agrees_with_parity_evaluator():
     assert (res[0][0].sum(1)[~live] == 0).all()
     same = (res[0][0].argmax(1) == res[1][0].argmax(1))[live].mean()
     assert same > 0.8
+
+
+def test_root_dirichlet_noise_formula_and_off_switch():
+    """exploration noise (self-play only): P <- (1-eps) P + eps * noise/sum(noise over legal)"""
+    from betazero_b200 import _lib, env, mcts
+    from oracle import pyoracle as po
+
+    B = 300
+    me_h, opp_h = po.playout_boards(B, seed=14)
+    pools = mcts.TreePools(B, 8)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(6), use_graph=False)
+    s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
+    s.run(1)  # expand the roots
+    _, _, P0 = (x.cpu().numpy() for x in s.root_edges())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    noise = torch.rand((B, 65), device="cuda", generator=g) + 0.01
+    _lib.check(_lib.load().bz_mcts_root_noise(pools._ref, _lib.dptr(noise), 0.25, _lib.stream_ptr()))
+    _, _, P1 = (x.cpu().numpy() for x in s.root_edges())
+    nz = noise.cpu().numpy()
+    legal = P0 > 0
+    exp = np.where(legal, 0.75 * P0 + 0.25 * nz / np.maximum((nz * legal).sum(1, keepdims=True), 1e-30), 0)
+    np.testing.assert_allclose(P1, exp, rtol=1e-5, atol=1e-7)
+    live = legal.any(1)
+    np.testing.assert_allclose(P1.sum(1)[live], 1.0, atol=1e-5)
+    # through the search API: alpha > 0 changes visit counts, alpha == 0 is bit-identical to the oracle
+    a = _search(me_h, opp_h, 64, salt=6)[1]
+    pools2 = mcts.TreePools(B, 64)
+    s2 = mcts.BatchedMCTS(pools2, mcts.HashEvaluator(6), use_graph=True, graph_unroll=8, dirichlet_alpha=0.3, noise_seed=5)
+    b = s2.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 64)[0].cpu().numpy()
+    assert (a.sum(1) == b.sum(1)).all() and (a != b).any()
+    r_cnt, _, _, _ = po.search_hash(me_h, opp_h, 64, po.GAME_REVERSI, 8, 1.25, 6)
+    assert np.array_equal(a, r_cnt)
+
+
+def test_resnet_through_net_evaluator():
+    from betazero_b200 import env, mcts, net
+    from oracle import pyoracle as po
+
+    B = 128
+    me_h, opp_h = po.playout_boards(B, seed=4)
+    model = net.make_net("resnet", channels=32, blocks=2, seed=0)
+    pools = mcts.TreePools(B, 24)
+    s = mcts.BatchedMCTS(pools, mcts.NetEvaluator(model), use_graph=True, graph_unroll=4)
+    cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 24)
+    live = po.terminal(me_h, opp_h)[0] == 0
+    assert (cnt.cpu().numpy().sum(1)[live] == 23).all()
+    assert torch.isfinite(pi).all() and torch.isfinite(q).all()
