@@ -392,12 +392,15 @@ def side_measurements(torch, env, hbm_peak):
     peak_int = ops / t3 * 1e3
     out["int32_peak"] = {"lane_ops_per_sec": peak_int, "ms": t3,
                          "note": "SHF+LOP3 mix (ALU pipe), 8 independent chains/thread, 148x8 CTAs x 256 threads"}
-    # instruction counts per board from the ncu capture in profiles/ (smsp__inst_executed x 32 / boards)
-    for key, inst in (("env_legal_mask", 216.6), ("env_step_first_legal", 432.1)):
-        out[key]["roofline"] = {"bound": "int32 ALU pipe", "inst_per_board": inst,
-                                "achieved_lane_ops_per_sec": out[key]["boards_per_sec"] * inst,
-                                "frac_of_measured_int32_peak": out[key]["boards_per_sec"] * inst / peak_int,
-                                "note": "all issued instructions counted; ~89-94 % of them are ALU-pipe (ncu: pipe_alu 89.2 % / 93.5 % busy)"}
+    # ALU-pipe utilisation and issued instructions per board come from the ncu capture committed in
+    # profiles/r1_env_kernels_raw.csv (sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,
+    # smsp__inst_executed.sum x 32 / boards); the issue rate below is measured live.
+    for key, inst, alu_frac in (("env_legal_mask", 216.6, 0.892), ("env_step_first_legal", 432.1, 0.935)):
+        out[key]["roofline"] = {"bound": "int32 ALU pipe", "frac": alu_frac, "frac_source": "ncu pipe_alu utilisation",
+                                "issued_inst_per_board": inst,
+                                "issued_lane_ops_per_sec": out[key]["boards_per_sec"] * inst,
+                                "measured_alu_pipe_peak_lane_ops_per_sec": peak_int,
+                                "note": "issued instructions include ~6 % IMAD/LDG/STG that do not use the ALU pipe"}
     return out
 
 
