@@ -27,6 +27,7 @@ def init(backend: str | None = None) -> tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         kw = {}
         if backend == "nccl":
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the caller's own output
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, rank=rank, world_size=world, **kw)
