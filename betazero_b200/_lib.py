@@ -53,6 +53,7 @@ _SP = C.POINTER(BzSelfplayState)
 SIGNATURES = {
     "bz_abi_version": [],
     "bz_error_string": [_INT],
+    "bz_set_pdl": [_INT],
     "bz_reversi_init": [ptr, ptr, ptr, _I64, _INT, ptr],
     "bz_reversi_legal_mask": [ptr, ptr, ptr, _I64, _INT, ptr],
     "bz_reversi_apply": [ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
@@ -132,3 +133,9 @@ def dptr(t):
     if not t.is_contiguous():
         raise BzError("expected a contiguous tensor")
     return C.c_void_p(t.data_ptr())
+
+
+def set_pdl(enable: bool) -> bool:
+    """Process-wide switch for programmatic dependent launch between the tree step kernel and the
+    fused MLP kernel (bz_set_pdl).  Returns the previous setting."""
+    return bool(load().bz_set_pdl(1 if enable else 0))

@@ -27,6 +27,31 @@ inline int persistent_grid(int64_t items, int threads, int ctas_per_sm) {
     return (int)(r <= need + kNumSMs / 2 ? r : need);
 }
 
+// Programmatic dependent launch (PDL): when enabled (bz_set_pdl), the tree step kernel and the fused MLP kernel
+// are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so the prologue of each (record / root
+// loads; TMEM allocation + first weight tile) overlaps the tail of the other instead of waiting for a full drain.
+// Both kernels execute griddepcontrol.wait before touching the other's output (a no-op without the attribute).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // streaming (read-once / write-once) 128-bit global accesses that do not allocate in L1

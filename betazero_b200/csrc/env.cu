@@ -262,7 +262,12 @@ __global__ void __launch_bounds__(kThreads) int32_bench_kernel(uint32_t *sink, i
 
 bool size_ok(int size) { return size == 4 || size == 6 || size == 8; }
 
+bool g_pdl = false;
+
 }  // namespace
+
+bool pdl_enabled() { return g_pdl; }
+
 }  // namespace bz
 
 using namespace bz;
@@ -270,6 +275,12 @@ using namespace bz;
 extern "C" {
 
 int bz_abi_version(void) { return BZ_ABI_VERSION; }
+
+int bz_set_pdl(int enable) {
+    const int old = g_pdl ? 1 : 0;
+    g_pdl = enable != 0;
+    return old;
+}
 
 const char *bz_error_string(int code) {
     if (code == BZ_OK) return "ok";

@@ -139,9 +139,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // layer-0 operands: the leaf planes and W1
-    load_operand(sA, kSlabA, p.x + (size_t)row0 * kIn, kRows, kIn, kIn, valid_rows);
+    // layer-0 operands: W1 does not depend on the previous kernel; the leaf planes do (PDL: wait for the tree
+    // kernel that wrote them, then let the next tree kernel start its own prologue)
     load_operand(sB, kSlabB, p.w[0], kHidden, kIn, kIn, kHidden);
+    pdl_wait();
+    pdl_launch_dependents();
+    load_operand(sA, kSlabA, p.x + (size_t)row0 * kIn, kRows, kIn, kIn, valid_rows);
     asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -258,6 +261,8 @@ extern "C" int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1
     p.w[3] = (const __nv_bfloat16 *)w_head; p.b[3] = (const __nv_bfloat16 *)b_head;
     p.out = (__nv_bfloat16 *)out_bf16;
     p.B = (int)n;
-    mlp_kernel<<<(unsigned)((n + kRows - 1) / kRows), kThreads, kSmemTotal, as_stream(stream)>>>(p);
+    cudaError_t e = launch_kernel(mlp_kernel, dim3((unsigned)((n + kRows - 1) / kRows)), dim3(kThreads), (size_t)kSmemTotal,
+                                  as_stream(stream), pdl_enabled(), p);
+    if (e != cudaSuccess) return cuda_rc(e);
     return launch_rc();
 }

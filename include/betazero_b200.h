@@ -44,6 +44,11 @@ extern "C" {
 typedef void *bz_stream_t; /* cudaStream_t */
 
 int bz_abi_version(void);
+
+/* Process-wide switch for programmatic dependent launch between bz_mcts_step and bz_mlp_forward
+ * (each kernel's prologue overlaps the other's tail; both wait on griddepcontrol before reading
+ * the other's output).  Returns the previous setting.  Off by default. */
+int bz_set_pdl(int enable);
 /* static string for a return code of this library (host) */
 const char *bz_error_string(int code);
 

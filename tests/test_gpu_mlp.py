@@ -78,3 +78,24 @@ def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
     live = po.terminal(me_h, opp_h)[0] == 0
     assert (res[0][0].sum(1)[live] == n_sims - 1).all()
     assert (res[0][0].argmax(1) == res[1][0].argmax(1))[live].mean() > 0.8
+
+
+def test_programmatic_dependent_launch_changes_nothing_but_time():
+    """bz_set_pdl: the step kernel and the fused MLP kernel overlap prologue/tail; results identical"""
+    from betazero_b200 import _lib, env, mcts, net
+    from oracle import pyoracle as po
+
+    B, n_sims = 512, 40
+    me_h, opp_h = po.playout_boards(B, seed=21)
+    model = net.make_net("mlp", seed=7)
+    out = []
+    try:
+        for pdl in (False, True):
+            assert _lib.set_pdl(pdl) in (True, False)
+            pools = mcts.TreePools(B, n_sims)
+            s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=True), use_graph=True, graph_unroll=8)
+            cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
+            out.append((cnt.clone(), q.clone()))
+    finally:
+        _lib.set_pdl(False)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
