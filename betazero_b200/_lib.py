@@ -78,6 +78,8 @@ SIGNATURES = {
     "bz_reversi_symmetry": [ptr, ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
     "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_forward": [ptr] * 10 + [_I64, _INT, _INT, _INT, _INT, ptr],
+    "bz_mlp_forward_packed": [ptr, ptr, ptr, ptr, _I64, ptr],
+    "bz_mlp_weight_image_bytes": [],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],
 }
 
@@ -107,7 +109,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "bz_error_string" else C.c_int
+        fn.restype = C.c_char_p if name == "bz_error_string" else (C.c_int64 if name.endswith("_bytes") else C.c_int)
     _lib = lib
     return lib
 

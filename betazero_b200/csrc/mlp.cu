@@ -234,6 +234,221 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
+
+// =====================================================================================================
+// v2: the same network as a warp-specialised pipeline.
+//   warp 0      MMA issuer (one thread): per layer, per N-half, per 64-wide K slab: 4 x tcgen05.mma
+//   warp 1      producer (one thread): streams the weights as 16 KB units (one N-half x one K slab) from a
+//               host-prepared image that already has the SWIZZLE_128B shared-memory layout, one
+//               cp.async.bulk per unit into a 4-stage ring (mbarrier complete_tx)
+//   warps 2-17  epilogue: 4 warps per TMEM lane quadrant, each owns 64 accumulator columns = one K slab of the
+//               NEXT layer's A operand: tcgen05.ld -> +bias, ReLU, bf16 -> swizzled st.shared -> arrive
+// Accumulators are double buffered in TMEM (2 x 256 columns) and activations in shared memory (2 x 64 KB), so
+// layer L+1's MMAs start on K slab s as soon as layer L's epilogue has produced it, and the epilogue of N-half 0
+// overlaps the MMAs of N-half 1.
+// =====================================================================================================
+constexpr int kEpiWarps = 16;
+constexpr int kThreads2 = (2 + kEpiWarps) * 32;
+constexpr int kUnitBytes = 128 * 128;           // 128 weight rows x one 64-element K slab
+constexpr int kHeadUnitBytes = kHeadRows * 128;  // the head has 80 rows
+constexpr int kStages = 4;
+constexpr int kNumUnits = 4 + 8 + 8 + 4;
+constexpr int kSmem2 = 2 * kSmemA + kStages * kUnitBytes + 512 + 1024;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct Mlp2Params {
+    const __nv_bfloat16 *x;     // [B, 128]
+    const uint8_t *wimg;        // kNumUnits x 16 KB, units in consumption order, SWIZZLE_128B image
+    const float *bias;          // [256 + 256 + 256 + 80] fp32
+    __nv_bfloat16 *out;         // [B, 72]
+    int B;
+};
+
+__global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t sA0 = base, sRing = base + 2 * kSmemA;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * kSmemA + kStages * kUnitBytes);
+    // barrier map: full[4] empty[4] a_ready[2][4] d_ready[2][2]
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(4 + i); };
+    auto AREADY = [&](int b, int sl) { return bar0 + 8u * (uint32_t)(8 + b * 4 + sl); };
+    auto DREADY = [&](int b, int h) { return bar0 + 8u * (uint32_t)(16 + b * 2 + h); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kRows;
+    const int valid_rows = min(kRows, p.B - row0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < 4; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(AREADY(i >> 2, i & 3), 4);  // one elected lane of each of the 4 quadrant warps
+        for (int i = 0; i < 4; ++i) mbar_init(DREADY(i >> 1, i & 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 1) {
+        // ---------------- producer: weights never depend on the previous kernel, start at once ----------------
+        if (lane == 0) {
+            for (int u = 0; u < kNumUnits; ++u) {
+                const int st = u & (kStages - 1);
+                if (u >= kStages) mbar_wait(EMPTY(st), (uint32_t)(((u / kStages) - 1) & 1));
+                const uint32_t bytes = u >= 20 ? kHeadUnitBytes : kUnitBytes;
+                mbar_expect_tx(FULL(st), bytes);
+                bulk_load(sRing + (uint32_t)st * kUnitBytes, p.wimg + (size_t)u * kUnitBytes, bytes, FULL(st));
+            }
+        }
+    } else if (warp == 0) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            uint32_t a_par = 0;  // bit (b*4+s): phase parity of a_ready[b][s]
+            int u = 0;
+            for (int L = 0; L < 4; ++L) {
+                const int b = L & 1, nh = L == 3 ? 1 : 2, ns = L == 0 ? 2 : 4, N = L == 3 ? kHeadRows : 128;
+                const uint32_t idesc = umma_idesc(kRows, N);
+                const uint32_t sA = sA0 + (uint32_t)b * kSmemA;
+                for (int h = 0; h < nh; ++h) {
+                    for (int sl = 0; sl < ns; ++sl, ++u) {
+                        const int st = u & (kStages - 1);
+                        mbar_wait(FULL(st), (uint32_t)((u / kStages) & 1));
+                        if (h == 0) {
+                            mbar_wait(AREADY(b, sl), (a_par >> (b * 4 + sl)) & 1u);
+                            a_par ^= 1u << (b * 4 + sl);
+                        }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t d = tmem + (uint32_t)(b * 256 + h * 128);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(d, umma_desc(sA + (uint32_t)sl * kSlabA + kk * 32u),
+                                      umma_desc(sRing + (uint32_t)st * kUnitBytes + kk * 32u), idesc, (sl | kk) != 0);
+                        umma_commit(EMPTY(st));  // the ring stage is free once these MMAs have read it
+                    }
+                    umma_commit(DREADY(b, h));  // accumulator half complete
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps ----------------
+        const int e = warp - 2;
+        const int q = warp & 3;   // TMEM lane quadrant this warp may access
+        const int cg = e >> 2;    // 64-column group == K slab of the next layer's A operand
+        const int r = q * 32 + lane;
+        // layer-0 input: the leaf planes (written by the previous kernel: PDL wait first)
+        pdl_wait();
+        pdl_launch_dependents();
+        if (cg < 2) {  // slab cg of A[0]: this warp loads its 32 rows x 8 chunks
+            const bool ok = r < valid_rows;
+            const __nv_bfloat16 *src = p.x + (size_t)(row0 + (ok ? r : 0)) * kIn + cg * 64;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                cp_async16(sA0 + (uint32_t)cg * kSlabA + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4), src + j * 8, ok);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(AREADY(0, cg));
+        }
+        uint32_t d_par = 0;  // bit b: parity of this warp's d_ready[b][h]
+        const int h = cg >> 1;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        for (int L = 0; L < 3; ++L) {
+            const int b = L & 1;
+            const float *bias = p.bias + L * kHidden;
+            mbar_wait(DREADY(b, h), (d_par >> b) & 1u);
+            d_par ^= 1u << b;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dstA = sA0 + (uint32_t)(b ^ 1) * kSmemA + (uint32_t)cg * kSlabA + (uint32_t)r * 128u;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int c0 = cg * 64 + half * 32;
+                uint32_t acc[32];
+                tmem_ld32(trow + (uint32_t)(b * 256 + c0), acc);
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + 4 * j);
+                    const float v0 = fmaxf(__uint_as_float(acc[4 * j + 0]) + bv.x, 0.f), v1 = fmaxf(__uint_as_float(acc[4 * j + 1]) + bv.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(acc[4 * j + 2]) + bv.z, 0.f), v3 = fmaxf(__uint_as_float(acc[4 * j + 3]) + bv.w, 0.f);
+                    packed[2 * j] = pack_bf16(v0, v1);
+                    packed[2 * j + 1] = pack_bf16(v2, v3);
+                }
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint32_t dst = dstA + (uint32_t)(((half * 4 + qq) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * qq]), "r"(packed[4 * qq + 1]),
+                                 "r"(packed[4 * qq + 2]), "r"(packed[4 * qq + 3])
+                                 : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(AREADY(b ^ 1, cg));
+        }
+        // head (layer 3, accumulator buffer 1, one N block of 80 columns): 72 output columns -> global
+        if (cg < 2) {
+            mbar_wait(DREADY(1, 0), (d_par >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float *bias = p.bias + 3 * kHidden;
+            __nv_bfloat16 *orow = p.out + (size_t)(row0 + r) * kOutStride;
+            for (int half = 0; half < 2; ++half) {
+                const int c0 = cg * 64 + half * 32;
+                if (c0 >= 96) break;  // warp-uniform
+                uint32_t acc[32];
+                tmem_ld32(trow + (uint32_t)(256 + c0), acc);  // columns >= 80 are stale: never stored
+                if (r < valid_rows) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int c = c0 + qq * 8;
+                        if (c < kOutStride) {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c), b1 = *reinterpret_cast<const float4 *>(bias + c + 4);
+                            uint4 v;
+                            v.x = pack_bf16(__uint_as_float(acc[qq * 8 + 0]) + b0.x, __uint_as_float(acc[qq * 8 + 1]) + b0.y);
+                            v.y = pack_bf16(__uint_as_float(acc[qq * 8 + 2]) + b0.z, __uint_as_float(acc[qq * 8 + 3]) + b0.w);
+                            v.z = pack_bf16(__uint_as_float(acc[qq * 8 + 4]) + b1.x, __uint_as_float(acc[qq * 8 + 5]) + b1.y);
+                            v.w = pack_bf16(__uint_as_float(acc[qq * 8 + 6]) + b1.z, __uint_as_float(acc[qq * 8 + 7]) + b1.w);
+                            *reinterpret_cast<uint4 *>(orow + c) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
 }  // namespace
 }  // namespace bz
 
@@ -266,3 +481,28 @@ extern "C" int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1
     if (e != cudaSuccess) return cuda_rc(e);
     return launch_rc();
 }
+
+extern "C" int bz_mlp_forward_packed(const void *x_bf16, const void *weight_image, const void *bias_f32, void *out_bf16,
+                                     int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!x_bf16 || !weight_image || !bias_f32 || !out_bf16))) return BZ_ERR_ARG;
+    if (!aligned16(x_bf16) || !aligned16(weight_image) || !aligned16(bias_f32) || !aligned16(out_bf16)) return BZ_ERR_UNALIGNED;
+    if (n == 0) return BZ_OK;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+        if (e != cudaSuccess) return cuda_rc(e);
+        configured = true;
+    }
+    Mlp2Params p;
+    p.x = (const __nv_bfloat16 *)x_bf16;
+    p.wimg = (const uint8_t *)weight_image;
+    p.bias = (const float *)bias_f32;
+    p.out = (__nv_bfloat16 *)out_bf16;
+    p.B = (int)n;
+    cudaError_t e = launch_kernel(mlp_pipe_kernel, dim3((unsigned)((n + kRows - 1) / kRows)), dim3(kThreads2), (size_t)kSmem2,
+                                  as_stream(stream), pdl_enabled(), p);
+    if (e != cudaSuccess) return cuda_rc(e);
+    return launch_rc();
+}
+
+extern "C" int64_t bz_mlp_weight_image_bytes(void) { return (int64_t)kNumUnits * kUnitBytes; }

@@ -18,6 +18,31 @@ N_ACTIONS = 65
 TTT_ACTIONS = 9
 
 
+def pack_mlp_weights(weights, biases):
+    """Weight image + bias vector for ``bz_mlp_forward_packed``: every 128-row x 64-column block of a
+    layer (80 rows for the head) becomes one 16 KB unit laid out exactly as the kernel wants it in
+    shared memory (K-major SWIZZLE_128B: 16-byte chunk j of row r at chunk j ^ (r & 7)), units in
+    consumption order (layer, N-half, K slab).  ``weights``: [W1 [256,128], W2, W3 [256,256],
+    W_head [80,256]] bf16; returns (uint8 [24, 16384], float32 [848])."""
+    units = []
+    for li, W in enumerate(weights):
+        N, K = W.shape
+        halves = 1 if li == 3 else 2
+        rows, ns = N // halves, K // 64
+        v = W.contiguous().view(halves, rows, ns, 8, 8).permute(0, 2, 1, 3, 4).contiguous()  # [h, s, r, j, e]
+        r = torch.arange(rows, device=W.device)[:, None]
+        j = torch.arange(8, device=W.device)[None, :]
+        src = (j ^ (r & 7))[None, None, :, :, None].expand(halves, ns, rows, 8, 8)
+        v = torch.gather(v, 3, src)  # position p of row r holds source chunk p ^ (r & 7)
+        u = v.reshape(halves * ns, rows * 64).view(torch.uint8)  # [units, rows*128 bytes]
+        pad = torch.zeros((u.shape[0], 16384), dtype=torch.uint8, device=W.device)
+        pad[:, : u.shape[1]] = u
+        units.append(pad)
+    image = torch.cat(units).contiguous()
+    bias = torch.cat([b.float().reshape(-1) for b in biases]).contiguous()
+    return image, bias
+
+
 class PolicyValueMLP(nn.Module):
     """in -> H -> H -> H -> (A logits, 1 value): TicTacToeNet (neural_networks.py:4-30) + value head."""
 
@@ -53,6 +78,11 @@ class PolicyValueMLP(nn.Module):
         self._head_full = (w.contiguous(), b.contiguous())
         self._head = (w[: self.raw_width], b[: self.raw_width])
         self._w = [m.weight.t() for m in (self.fc1, self.fc2, self.fc3)]
+        self._packed = None
+        if w.is_cuda and w.dtype == torch.bfloat16 and self.fc1.in_features == 128 and self.fc1.out_features == 256 \
+                and self.raw_width == 72:
+            self._packed = pack_mlp_weights([self.fc1.weight, self.fc2.weight, self.fc3.weight, w[:80]],
+                                            [self.fc1.bias, self.fc2.bias, self.fc3.bias, b[:80]])
 
     def fused_kernel_ok(self, planes: torch.Tensor) -> bool:
         """the hand-written tcgen05 kernel covers exactly the Reversi shape in bf16 on a GPU"""
@@ -61,7 +91,7 @@ class PolicyValueMLP(nn.Module):
                 and not self.training)
 
     @torch.no_grad()
-    def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None, fused: bool | None = None) -> torch.Tensor:
+    def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None, fused: bool | str | None = None) -> torch.Tensor:
         """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A.
 
         Default: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.  ``fused=True``
@@ -78,6 +108,12 @@ class PolicyValueMLP(nn.Module):
 
             if out is None:
                 out = torch.empty((B, self.raw_width), dtype=torch.bfloat16, device=planes.device)
+            if fused != "v1" and self._packed is not None:  # the pipelined kernel on the pre-swizzled weight image
+                img, bias = self._packed
+                L = _lib.load()
+                _lib.check(L.bz_mlp_forward_packed(_lib.dptr(planes.reshape(B, -1)), _lib.dptr(img), _lib.dptr(bias),
+                                                   _lib.dptr(out), B, _lib.stream_ptr()), "bz_mlp_forward_packed")
+                return out
             hw, hb = self._head_full
             x = planes.reshape(B, -1)
             L = _lib.load()

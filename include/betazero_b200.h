@@ -313,6 +313,17 @@ int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const voi
                    const void *w3, const void *b3, const void *w_head, const void *b_head, void *out_bf16,
                    int64_t n, int in_features, int hidden, int head_rows, int out_stride, bz_stream_t stream);
 
+/* The same network as a warp-specialised, software-pipelined kernel (MMA issuer / weight producer /
+ * 16 epilogue warps; TMEM and activation double buffering, cp.async.bulk weight streaming).
+ * weight_image: bz_mlp_weight_image_bytes() bytes = 24 units of 16 KB in consumption order
+ * (layer 0: 2 N-halves x 2 K slabs; layers 1, 2: 2 x 4; head: 4 K slabs of 80 rows), every unit already
+ * in the K-major SWIZZLE_128B shared-memory layout: 16-byte chunk j of weight row r sits at chunk
+ * j ^ (r & 7) of its 128-byte row (betazero_b200.net.pack_mlp_weights builds it).
+ * bias_f32: float32 [256 + 256 + 256 + 80].  x / out as in bz_mlp_forward. */
+int bz_mlp_forward_packed(const void *x_bf16, const void *weight_image, const void *bias_f32, void *out_bf16,
+                          int64_t n, bz_stream_t stream);
+int64_t bz_mlp_weight_image_bytes(void);
+
 /* INT32 issue-rate microbenchmark for the env roofline denominators.
  * variant 0: SHF + LOP3 chains, all on the ALU pipe (how 64-bit shifts/masks normally compile);
  * variant 1: the same 64-bit shift+mask work with shifts as IMAD (FMA pipe) and masks as LOP3 (ALU pipe).

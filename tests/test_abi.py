@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "betazero_b200.h")
 def _declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|const char \*)\s*(bz_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|int64_t|const char \*)\s*(bz_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported_and_bound():
