@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--net", default="mlp", choices=["mlp", "resnet"])
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--graph-unroll", type=int, default=16)
+    ap.add_argument("--mlp-kernel", action="store_true",
+                    help="evaluate the net with the hand-written tcgen05 MLP kernel + programmatic dependent launch "
+                         "instead of the PyTorch/cuBLASLt GEMMs (default: PyTorch, as the north-star specifies)")
     ap.add_argument("--cpu-trees", type=int, default=256, help="trees of the CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,6 +169,7 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
+            "net_backend": "bz_mlp_forward (tcgen05) + PDL" if getattr(args, "mlp_kernel", False) else "PyTorch/cuBLASLt",
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -197,7 +201,13 @@ def run_b200(args):
 
     B, S = args.games, args.sims
     net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
-    evaluator = mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
+    if args.mlp_kernel and hasattr(net, "forward_raw"):
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(True)
+        evaluator = mcts.FusedNetEvaluator(net, use_kernel=True)
+    else:
+        evaluator = mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
     sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
                                   graph_unroll=args.graph_unroll)
     sp.prepare()

@@ -251,7 +251,10 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads2 = (2 + kEpiWarps) * 32;
 constexpr int kUnitBytes = 128 * 128;           // 128 weight rows x one 64-element K slab
 constexpr int kHeadUnitBytes = kHeadRows * 128;  // the head has 80 rows
-constexpr int kStages = 4;
+#ifndef BZ_MLP_STAGES
+#define BZ_MLP_STAGES 6
+#endif
+constexpr int kStages = BZ_MLP_STAGES;  // 16 KB each; 6 = all the shared memory left beside the two activation buffers
 constexpr int kNumUnits = 4 + 8 + 8 + 4;
 constexpr int kSmem2 = 2 * kSmemA + kStages * kUnitBytes + 512 + 1024;
 
@@ -273,6 +276,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+#ifdef BZ_MLP_TRACE
+// debug timeline of CTA 0 (clock64 at key events); built only for profiling experiments
+__device__ long long g_mlp_trace[64];
+#define MLP_TRACE(i) do { if (blockIdx.x == 0) g_mlp_trace[i] = clock64(); } while (0)
+#else
+#define MLP_TRACE(i) do { } while (0)
+#endif
+
 struct Mlp2Params {
     const __nv_bfloat16 *x;     // [B, 128]
     const uint8_t *wimg;        // kNumUnits x 16 KB, units in consumption order, SWIZZLE_128B image
@@ -288,13 +299,13 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
     uint8_t *smem = smem_raw + (base - raw);
     const uint32_t sA0 = base, sRing = base + 2 * kSmemA;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * kSmemA + kStages * kUnitBytes);
-    // barrier map: full[4] empty[4] a_ready[2][4] d_ready[2][2]
+    // barrier map: full[kStages] empty[kStages] a_ready[2][4] d_ready[2][2]
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(4 + i); };
-    auto AREADY = [&](int b, int sl) { return bar0 + 8u * (uint32_t)(8 + b * 4 + sl); };
-    auto DREADY = [&](int b, int h) { return bar0 + 8u * (uint32_t)(16 + b * 2 + h); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+    auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(kStages + i); };
+    auto AREADY = [&](int b, int sl) { return bar0 + 8u * (uint32_t)(2 * kStages + b * 4 + sl); };
+    auto DREADY = [&](int b, int h) { return bar0 + 8u * (uint32_t)(2 * kStages + 8 + b * 2 + h); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRows;
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 32) {
-        for (int i = 0; i < 4; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
         for (int i = 0; i < 8; ++i) mbar_init(AREADY(i >> 2, i & 3), 4);  // one elected lane of each of the 4 quadrant warps
         for (int i = 0; i < 4; ++i) mbar_init(DREADY(i >> 1, i & 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -314,12 +325,13 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) MLP_TRACE(0);
 
     if (warp == 1) {
         // ---------------- producer: weights never depend on the previous kernel, start at once ----------------
         if (lane == 0) {
             for (int u = 0; u < kNumUnits; ++u) {
-                const int st = u & (kStages - 1);
+                const int st = u % kStages;
                 if (u >= kStages) mbar_wait(EMPTY(st), (uint32_t)(((u / kStages) - 1) & 1));
                 const uint32_t bytes = u >= 20 ? kHeadUnitBytes : kUnitBytes;
                 mbar_expect_tx(FULL(st), bytes);
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
                 const uint32_t sA = sA0 + (uint32_t)b * kSmemA;
                 for (int h = 0; h < nh; ++h) {
                     for (int sl = 0; sl < ns; ++sl, ++u) {
-                        const int st = u & (kStages - 1);
+                        const int st = u % kStages;
                         mbar_wait(FULL(st), (uint32_t)((u / kStages) & 1));
                         if (h == 0) {
                             mbar_wait(AREADY(b, sl), (a_par >> (b * 4 + sl)) & 1u);
@@ -352,6 +364,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
                         umma_commit(EMPTY(st));  // the ring stage is free once these MMAs have read it
                     }
                     umma_commit(DREADY(b, h));  // accumulator half complete
+                    MLP_TRACE(1 + L * 2 + h);  // MMA issue of (L, h) finished
                 }
             }
         }
@@ -374,6 +387,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(AREADY(0, cg));
+            if (e == 0 && lane == 0) MLP_TRACE(10);  // x loaded
         }
         uint32_t d_par = 0;  // bit b: parity of this warp's d_ready[b][h]
         const int h = cg >> 1;
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
             mbar_wait(DREADY(b, h), (d_par >> b) & 1u);
             d_par ^= 1u << b;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0 && (e == 0 || e == 8)) MLP_TRACE(11 + L * 4 + (e ? 2 : 0));  // D ready seen by epilogue (h0 / h1)
             const uint32_t dstA = sA0 + (uint32_t)(b ^ 1) * kSmemA + (uint32_t)cg * kSlabA + (uint32_t)r * 128u;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -411,6 +426,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(AREADY(b ^ 1, cg));
+            if (lane == 0 && (e == 0 || e == 8)) MLP_TRACE(12 + L * 4 + (e ? 2 : 0));  // epilogue slab done
         }
         // head (layer 3, accumulator buffer 1, one N block of 80 columns): 72 output columns -> global
         if (cg < 2) {
@@ -443,6 +459,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mlp_pipe_kernel(const Mlp2Params
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) MLP_TRACE(30);
     if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -506,3 +523,9 @@ extern "C" int bz_mlp_forward_packed(const void *x_bf16, const void *weight_imag
 }
 
 extern "C" int64_t bz_mlp_weight_image_bytes(void) { return (int64_t)kNumUnits * kUnitBytes; }
+
+#ifdef BZ_MLP_TRACE
+extern "C" int bz_mlp_debug_trace(long long *host_out) {
+    return cuda_rc(cudaMemcpyFromSymbol(host_out, g_mlp_trace, sizeof(long long) * 64));
+}
+#endif

@@ -95,9 +95,11 @@ class PolicyValueMLP(nn.Module):
         """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A.
 
         Default: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.  ``fused=True``
-        runs the hand-written single-launch tcgen05 kernel (``bz_mlp_forward``) instead; measured on
-        B200 at 4096 rows it is on par with the four library GEMMs (13.6 vs 12.6 us, 32 CTAs against
-        128-CTA GEMMs), so it is opt-in (profiles/README.md)."""
+        runs the hand-written single-launch tcgen05 kernel (``bz_mlp_forward``) instead, ``fused="v2"``
+        its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).  Measured on B200
+        at 4096 rows per MCTS iteration: library 22.6 us, v1 22.9 us (21.5 us with programmatic
+        dependent launch, ``_lib.set_pdl``), v2 24.7 / 23.5 us -- one CTA per 128 rows has to pull all
+        364 KB of weights through one SM, so the kernels are opt-in (profiles/README.md)."""
         if self._head is None:
             self.prepare_inference()
         B = planes.shape[0]
@@ -108,7 +110,7 @@ class PolicyValueMLP(nn.Module):
 
             if out is None:
                 out = torch.empty((B, self.raw_width), dtype=torch.bfloat16, device=planes.device)
-            if fused != "v1" and self._packed is not None:  # the pipelined kernel on the pre-swizzled weight image
+            if fused == "v2" and self._packed is not None:  # the pipelined kernel on the pre-swizzled weight image
                 img, bias = self._packed
                 L = _lib.load()
                 _lib.check(L.bz_mlp_forward_packed(_lib.dptr(planes.reshape(B, -1)), _lib.dptr(img), _lib.dptr(bias),
