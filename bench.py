@@ -323,9 +323,11 @@ def run_b200(args):
         }
         if not args.no_extra and world == 1:
             line["extra"] = side_measurements(torch, env, peak)
+            del sp
+            torch.cuda.empty_cache()
+            if not args.mlp_kernel and hasattr(net, "fused_kernel_ok"):
+                line["extra"]["mlp_kernel_pdl"] = alt_backend(torch, mcts, selfplay, net, args)
             if args.scale_games and args.scale_games != B:
-                del sp
-                torch.cuda.empty_cache()
                 line["extra"]["at_scale"] = at_scale(torch, mcts, selfplay, net, args, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay_sample(
@@ -335,6 +337,36 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def alt_backend(torch, mcts, selfplay, net, args):
+    """The headline workload with the net evaluated by the hand-written tcgen05 MLP kernel and programmatic
+    dependent launch between it and the tree kernel (opt-in: `--mlp-kernel`)."""
+    from betazero_b200 import _lib as bzlib
+
+    try:
+        bzlib.set_pdl(True)
+        sp = selfplay.BatchedSelfPlay(args.games, args.sims, mcts.FusedNetEvaluator(net, use_kernel=True), temp_plies=8,
+                                      seed=1234, graph_unroll=args.graph_unroll)
+        sp.prepare()
+        for _ in range(3):
+            sp.play_move()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        n = 10
+        for _ in range(n):
+            sp.play_move()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        sp.mcts.check_errors()
+        return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms,
+                "net_backend": "bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        bzlib.set_pdl(False)
 
 
 def at_scale(torch, mcts, selfplay, net, args, hbm_peak):
