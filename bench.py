@@ -39,9 +39,9 @@ def parse():
     ap.add_argument("--net", default="mlp", choices=["mlp", "resnet"])
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--graph-unroll", type=int, default=16)
-    ap.add_argument("--mlp-kernel", action="store_true",
-                    help="evaluate the net with the hand-written tcgen05 MLP kernel + programmatic dependent launch "
-                         "instead of the PyTorch/cuBLASLt GEMMs (default: PyTorch, as the north-star specifies)")
+    ap.add_argument("--torch-net", action="store_true",
+                    help="evaluate the net with PyTorch/cuBLASLt GEMMs (4 launches) instead of the default: the "
+                         "hand-written single-launch tcgen05 MLP kernel + programmatic dependent launch")
     ap.add_argument("--cpu-trees", type=int, default=256, help="trees of the CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -169,7 +169,8 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
-            "net_backend": "bz_mlp_forward (tcgen05) + PDL" if getattr(args, "mlp_kernel", False) else "PyTorch/cuBLASLt",
+            "net_backend": ("bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch"
+                            if getattr(args, "kernel_net", False) else "PyTorch/cuBLASLt GEMMs"),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -201,13 +202,13 @@ def run_b200(args):
 
     B, S = args.games, args.sims
     net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
-    if args.mlp_kernel and hasattr(net, "forward_raw"):
-        from betazero_b200 import _lib as bzlib
-
-        bzlib.set_pdl(True)
-        evaluator = mcts.FusedNetEvaluator(net, use_kernel=True)
+    kernel_net = (not args.torch_net) and hasattr(net, "fused_kernel_ok") and net.fused_kernel_ok(
+        torch.empty((1, 2, 8, 8), dtype=torch.bfloat16, device="cuda")) and B <= 148 * 128
+    args.kernel_net = kernel_net
+    if hasattr(net, "forward_raw"):
+        evaluator = mcts.FusedNetEvaluator(net, use_kernel=None if kernel_net else False)
     else:
-        evaluator = mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
+        evaluator = mcts.NetEvaluator(net)
     sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
                                   graph_unroll=args.graph_unroll)
     sp.prepare()
@@ -325,8 +326,8 @@ def run_b200(args):
             line["extra"] = side_measurements(torch, env, peak)
             del sp
             torch.cuda.empty_cache()
-            if not args.mlp_kernel and hasattr(net, "fused_kernel_ok"):
-                line["extra"]["mlp_kernel_pdl"] = alt_backend(torch, mcts, selfplay, net, args)
+            if hasattr(net, "forward_raw"):
+                line["extra"]["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
             if args.scale_games and args.scale_games != B:
                 line["extra"]["at_scale"] = at_scale(torch, mcts, selfplay, net, args, peak)
         if not args.no_cpu_baseline and world == 1:
@@ -340,14 +341,15 @@ def run_b200(args):
 
 
 def alt_backend(torch, mcts, selfplay, net, args):
-    """The headline workload with the net evaluated by the hand-written tcgen05 MLP kernel and programmatic
-    dependent launch between it and the tree kernel (opt-in: `--mlp-kernel`)."""
+    """The headline workload with the OTHER net backend (library GEMMs if the headline used the tcgen05 MLP
+    kernel, and vice versa), so one bench line shows both."""
     from betazero_b200 import _lib as bzlib
 
+    use_kernel = not getattr(args, "kernel_net", False)
     try:
-        bzlib.set_pdl(True)
-        sp = selfplay.BatchedSelfPlay(args.games, args.sims, mcts.FusedNetEvaluator(net, use_kernel=True), temp_plies=8,
-                                      seed=1234, graph_unroll=args.graph_unroll)
+        ev = mcts.FusedNetEvaluator(net, use_kernel=True if use_kernel else False)
+        bzlib.set_pdl(use_kernel)
+        sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll)
         sp.prepare()
         for _ in range(3):
             sp.play_move()
@@ -362,7 +364,8 @@ def alt_backend(torch, mcts, selfplay, net, args):
         ms = e0.elapsed_time(e1) / n
         sp.mcts.check_errors()
         return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms,
-                "net_backend": "bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch"}
+                "net_backend": ("bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch" if use_kernel
+                                else "PyTorch/cuBLASLt GEMMs")}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
     finally:

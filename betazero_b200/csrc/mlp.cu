@@ -21,7 +21,7 @@ constexpr int kIn = 128;         // 2 x 8 x 8 canonical planes
 constexpr int kHidden = 256;
 constexpr int kHeadRows = 80;    // 65 logits + value, padded to a legal UMMA N (multiple of 16)
 constexpr int kOutStride = 72;   // row stride of the output (multiple of 8 elements: 16-byte rows)
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;       // 16 warps: 4 per TMEM lane quadrant, each owns 64 accumulator columns in the epilogue
 constexpr int kSlabA = kRows * 128;      // one 64-element K slab of A: 128 rows x 128 B
 constexpr int kSlabB = kHidden * 128;    // one K slab of B: 256 rows x 128 B
 constexpr int kSmemA = 4 * kSlabA;       // 64 KB
@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
             const int nextN = layer == 2 ? kHeadRows : kHidden;
             load_operand(sB, kSlabB, p.w[layer + 1], nextN, kHidden, kHidden, nextN);
         }
-        // epilogue: thread <-> accumulator row; warp w reads TMEM lanes 32*(w%4).., column half w/4
+        // epilogue: thread <-> accumulator row; warp w reads TMEM lanes 32*(w%4).., column quarter w/4
         const int r = (warp & 3) * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         if (layer < 3) {
-            const int c_begin = (warp >> 2) * (kHidden / 2);
+            const int c_begin = (warp >> 2) * (kHidden / 4);
 #pragma unroll 1
-            for (int c0 = c_begin; c0 < c_begin + kHidden / 2; c0 += 32) {
+            for (int c0 = c_begin; c0 < c_begin + kHidden / 4; c0 += 32) {
                 uint32_t acc[32];
                 tmem_ld32(trow + (uint32_t)c0, acc);
                 uint32_t packed[16];
@@ -205,11 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        } else if (warp < 4) {
-            // head: 72 output columns (65 logits, value, padding) -> global, bf16, no activation
+        } else if (warp < 12) {
+            // head: 72 output columns (65 logits, value, padding) -> global, bf16, no activation;
+            // column group w/4 takes one 32-column chunk
             __nv_bfloat16 *orow = p.out + (size_t)(row0 + r) * kOutStride;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 96; c0 += 32) {
+            {
+                const int c0 = (warp >> 2) * 32;
                 uint32_t acc[32];
                 tmem_ld32(trow + (uint32_t)c0, acc);  // columns >= 80 of the last chunk are stale accumulators: never stored
                 if (r < valid_rows) {

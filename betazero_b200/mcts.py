@@ -168,11 +168,16 @@ class FusedNetEvaluator:
 
     prior_mode = PRIOR_LOGITS_BF16
 
-    def __init__(self, net: torch.nn.Module, use_kernel: bool | None = None):
+    def __init__(self, net: torch.nn.Module, use_kernel: bool | str | None = None, pdl: bool | None = None):
         if not hasattr(net, "forward_raw"):
             raise TypeError("FusedNetEvaluator needs a net with forward_raw()")
         self.net = net
-        self.use_kernel = use_kernel  # True: the single-launch tcgen05 MLP kernel (bz_mlp_forward); default library GEMMs
+        # None: the single-launch tcgen05 MLP kernel (bz_mlp_forward) when shape and batch allow, else
+        # the library GEMMs; True / "v2" / False force one path
+        self.use_kernel = use_kernel
+        # programmatic dependent launch between the MLP kernel and the tree step kernel (process-wide
+        # switch, results identical): on by default whenever the kernel path may be taken
+        self.pdl = (use_kernel is not False) if pdl is None else bool(pdl)
 
     def bind(self, pools: "TreePools"):
         B = max(pools.n_trees, 1)
@@ -181,6 +186,8 @@ class FusedNetEvaluator:
         self.value = torch.zeros(1, dtype=torch.float32, device=pools.device)  # unused in this mode
         pools.set_prior_mode(PRIOR_LOGITS_BF16, self.stride)
         self.refresh()
+        if self.pdl:
+            _lib.set_pdl(True)
         return self.out, self.value
 
     def refresh(self) -> None:

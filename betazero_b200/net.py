@@ -94,17 +94,18 @@ class PolicyValueMLP(nn.Module):
     def forward_raw(self, planes: torch.Tensor, out: torch.Tensor | None = None, fused: bool | str | None = None) -> torch.Tensor:
         """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A.
 
-        Default: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.  ``fused=True``
-        runs the hand-written single-launch tcgen05 kernel (``bz_mlp_forward``) instead, ``fused="v2"``
-        its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).  Measured on B200
-        at 4096 rows per MCTS iteration: library 22.6 us, v1 22.9 us (21.5 us with programmatic
-        dependent launch, ``_lib.set_pdl``), v2 24.7 / 23.5 us -- one CTA per 128 rows has to pull all
-        364 KB of weights through one SM, so the kernels are opt-in (profiles/README.md)."""
+        ``fused=False``: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.
+        ``fused=True``: the hand-written single-launch tcgen05 kernel (``bz_mlp_forward``);
+        ``fused="v2"``: its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).
+        ``fused=None`` (default) picks the kernel for the supported shape when the batch fits one wave
+        of 128-row CTAs (<= 18944 rows), else the library GEMMs.  Measured on B200 at 4096 rows, per
+        MCTS iteration: library 22.4 us, kernel 22.6 us, kernel + programmatic dependent launch
+        (``_lib.set_pdl``) 20.3 us, v2 24.7 / 23.5 us (profiles/README.md)."""
         if self._head is None:
             self.prepare_inference()
         B = planes.shape[0]
-        if fused is None:
-            fused = False
+        if fused is None:  # auto: the single-launch kernel while one wave of 128-row CTAs covers the batch
+            fused = self.fused_kernel_ok(planes) and B <= 148 * 128
         if fused:
             from . import _lib
 
