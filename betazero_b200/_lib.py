@@ -78,6 +78,7 @@ SIGNATURES = {
     "bz_reversi_symmetry": [ptr, ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
     "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_forward": [ptr] * 10 + [_I64, _INT, _INT, _INT, _INT, ptr],
+    "bz_mlp_forward_image": [ptr] * 7 + [_I64, ptr],
     "bz_mlp_forward_packed": [ptr, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_weight_image_bytes": [],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],

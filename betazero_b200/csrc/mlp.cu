@@ -27,7 +27,7 @@ constexpr int kSlabB = kHidden * 128;    // one K slab of B: 256 rows x 128 B
 constexpr int kSmemA = 4 * kSlabA;       // 64 KB
 constexpr int kSmemB = 4 * kSlabB;       // 128 KB
 constexpr int kSmemBias = kHidden * 4;   // 1 KB
-constexpr int kSmemTotal = kSmemA + kSmemB + kSmemBias + 64 + 1024;  // + barrier/tmem slot + alignment slack
+constexpr int kSmemTotal = kSmemA + kSmemB + kSmemBias + 64 + 1024;  // + barriers/tmem slot + alignment slack
 constexpr int kTmemCols = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,12 +91,34 @@ __device__ __forceinline__ void load_operand(uint32_t sbase, int slab_bytes, con
     }
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 struct MlpParams {
     const __nv_bfloat16 *x;                 // [B, 128]
     const __nv_bfloat16 *w[4], *b[4];       // [256,128] [256,256] [256,256] [80,256]; biases 256/256/256/80
     __nv_bfloat16 *out;                     // [B, 72]
     int B;
+    const uint8_t *wimg;                    // optional: 14 units of 32 KB (layer, K slab) already in the shared-memory
+                                            // layout -> weights arrive by cp.async.bulk (TMA) instead of 16-byte LDGSTS
 };
+
+__device__ __forceinline__ int image_unit_of_layer(int layer) { return layer == 0 ? 0 : 2 + (layer - 1) * 4; }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -123,8 +145,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
     const uint32_t sA = base, sB = base + kSmemA;
     float *sBias = reinterpret_cast<float *>(smem + kSmemA + kSmemB);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kSmemA + kSmemB + kSmemBias);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
-    const uint32_t bar_addr = smem_u32(bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
+    const uint32_t bar_addr = smem_u32(bar), wbar_addr = smem_u32(bar + 1);
+    const bool bulk = p.wimg != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRows;
@@ -136,12 +159,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 32) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+        mbar_init(bar_addr, 1);
+        mbar_init(wbar_addr, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (bulk) {  // W1: two 32 KB K slabs, one bulk copy
+            mbar_expect_tx(wbar_addr, 2 * kSlabB);
+            bulk_load(sB, p.wimg, 2 * kSlabB, wbar_addr);
+        }
     }
     // layer-0 operands: W1 does not depend on the previous kernel; the leaf planes do (PDL: wait for the tree
     // kernel that wrote them, then let the next tree kernel start its own prologue)
-    load_operand(sB, kSlabB, p.w[0], kHidden, kIn, kIn, kHidden);
+    if (!bulk) load_operand(sB, kSlabB, p.w[0], kHidden, kIn, kIn, kHidden);
     pdl_wait();
     pdl_launch_dependents();
     load_operand(sA, kSlabA, p.x + (size_t)row0 * kIn, kRows, kIn, kIn, valid_rows);
@@ -157,6 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
         const int K = layer == 0 ? kIn : kHidden;
         const int N = layer == 3 ? kHeadRows : kHidden;
         if (threadIdx.x == 0) {
+            if (bulk) {  // this layer's weights were sent by cp.async.bulk: wait for them to land
+                mbar_wait(wbar_addr, (uint32_t)(layer & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             const uint32_t idesc = umma_idesc(kRows, N);
             for (int k = 0; k < K / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
                 const uint32_t off = (uint32_t)(k >> 2), kk = (uint32_t)(k & 3) * 32u;
@@ -171,7 +203,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpParams p) {
         __syncthreads();  // bias visible; A and B are free again (the MMAs have read them)
         if (layer < 3) {  // next layer's weights stream in while the epilogue runs
             const int nextN = layer == 2 ? kHeadRows : kHidden;
-            load_operand(sB, kSlabB, p.w[layer + 1], nextN, kHidden, kHidden, nextN);
+            if (!bulk) {
+                load_operand(sB, kSlabB, p.w[layer + 1], nextN, kHidden, kHidden, nextN);
+            } else if (threadIdx.x == 32) {
+                const uint8_t *src = p.wimg + (size_t)image_unit_of_layer(layer + 1) * kSlabB;
+                if (layer + 1 < 3) {  // four 32 KB K slabs, contiguous in the image and in shared memory
+                    mbar_expect_tx(wbar_addr, 4 * kSlabB);
+                    bulk_load(sB, src, 4 * kSlabB, wbar_addr);
+                } else {  // head: 80 rows per slab
+                    mbar_expect_tx(wbar_addr, 4 * kHeadRows * 128);
+                    for (int sl = 0; sl < 4; ++sl) bulk_load(sB + sl * kSlabB, src + (size_t)sl * kSlabB, kHeadRows * 128, wbar_addr);
+                }
+            }
         }
         // epilogue: thread <-> accumulator row; warp w reads TMEM lanes 32*(w%4).., column quarter w/4
         const int r = (warp & 3) * 32 + lane;
@@ -258,24 +301,6 @@ constexpr int kHeadUnitBytes = kHeadRows * 128;  // the head has 80 rows
 constexpr int kStages = BZ_MLP_STAGES;  // 16 KB each; 6 = all the shared memory left beside the two activation buffers
 constexpr int kNumUnits = 4 + 8 + 8 + 4;
 constexpr int kSmem2 = 2 * kSmemA + kStages * kUnitBytes + 512 + 1024;
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 #ifdef BZ_MLP_TRACE
 // debug timeline of CTA 0 (clock64 at key events); built only for profiling experiments
@@ -494,6 +519,7 @@ extern "C" int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1
     p.w[3] = (const __nv_bfloat16 *)w_head; p.b[3] = (const __nv_bfloat16 *)b_head;
     p.out = (__nv_bfloat16 *)out_bf16;
     p.B = (int)n;
+    p.wimg = nullptr;
     cudaError_t e = launch_kernel(mlp_kernel, dim3((unsigned)((n + kRows - 1) / kRows)), dim3(kThreads), (size_t)kSmemTotal,
                                   as_stream(stream), pdl_enabled(), p);
     if (e != cudaSuccess) return cuda_rc(e);
@@ -530,3 +556,29 @@ extern "C" int bz_mlp_debug_trace(long long *host_out) {
     return cuda_rc(cudaMemcpyFromSymbol(host_out, g_mlp_trace, sizeof(long long) * 64));
 }
 #endif
+
+// bz_mlp_forward with TMA weight streaming: biases as in bz_mlp_forward (bf16), weights as an image of 14 units of
+// 32 KB (layer 0: 2 K slabs, layers 1 and 2: 4, head: 4 with 80 rows each), each unit in the shared-memory layout
+extern "C" int bz_mlp_forward_image(const void *x_bf16, const void *weight_image32, const void *b1, const void *b2, const void *b3,
+                                    const void *b_head, void *out_bf16, int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!x_bf16 || !weight_image32 || !b1 || !b2 || !b3 || !b_head || !out_bf16))) return BZ_ERR_ARG;
+    if (!aligned16(x_bf16) || !aligned16(weight_image32) || !aligned16(out_bf16)) return BZ_ERR_UNALIGNED;
+    if (n == 0) return BZ_OK;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        if (e != cudaSuccess) return cuda_rc(e);
+        configured = true;
+    }
+    MlpParams p = {};
+    p.x = (const __nv_bfloat16 *)x_bf16;
+    p.b[0] = (const __nv_bfloat16 *)b1; p.b[1] = (const __nv_bfloat16 *)b2;
+    p.b[2] = (const __nv_bfloat16 *)b3; p.b[3] = (const __nv_bfloat16 *)b_head;
+    p.out = (__nv_bfloat16 *)out_bf16;
+    p.B = (int)n;
+    p.wimg = (const uint8_t *)weight_image32;
+    cudaError_t e = launch_kernel(mlp_kernel, dim3((unsigned)((n + kRows - 1) / kRows)), dim3(kThreads), (size_t)kSmemTotal,
+                                  as_stream(stream), pdl_enabled(), p);
+    if (e != cudaSuccess) return cuda_rc(e);
+    return launch_rc();
+}

@@ -18,16 +18,17 @@ N_ACTIONS = 65
 TTT_ACTIONS = 9
 
 
-def pack_mlp_weights(weights, biases):
+def pack_mlp_weights(weights, biases, split_halves: bool = True):
     """Weight image + bias vector for ``bz_mlp_forward_packed``: every 128-row x 64-column block of a
     layer (80 rows for the head) becomes one 16 KB unit laid out exactly as the kernel wants it in
     shared memory (K-major SWIZZLE_128B: 16-byte chunk j of row r at chunk j ^ (r & 7)), units in
     consumption order (layer, N-half, K slab).  ``weights``: [W1 [256,128], W2, W3 [256,256],
-    W_head [80,256]] bf16; returns (uint8 [24, 16384], float32 [848])."""
+    W_head [80,256]] bf16; returns (uint8 [24, 16384], float32 [848]).  ``split_halves=False`` keeps
+    all 256 rows of a K slab together (14 units of 32 KB: the image of ``bz_mlp_forward_image``)."""
     units = []
     for li, W in enumerate(weights):
         N, K = W.shape
-        halves = 1 if li == 3 else 2
+        halves = 1 if (li == 3 or not split_halves) else 2
         rows, ns = N // halves, K // 64
         v = W.contiguous().view(halves, rows, ns, 8, 8).permute(0, 2, 1, 3, 4).contiguous()  # [h, s, r, j, e]
         r = torch.arange(rows, device=W.device)[:, None]
@@ -35,7 +36,7 @@ def pack_mlp_weights(weights, biases):
         src = (j ^ (r & 7))[None, None, :, :, None].expand(halves, ns, rows, 8, 8)
         v = torch.gather(v, 3, src)  # position p of row r holds source chunk p ^ (r & 7)
         u = v.reshape(halves * ns, rows * 64).view(torch.uint8)  # [units, rows*128 bytes]
-        pad = torch.zeros((u.shape[0], 16384), dtype=torch.uint8, device=W.device)
+        pad = torch.zeros((u.shape[0], 16384 if split_halves else 32768), dtype=torch.uint8, device=W.device)
         pad[:, : u.shape[1]] = u
         units.append(pad)
     image = torch.cat(units).contiguous()
@@ -81,8 +82,10 @@ class PolicyValueMLP(nn.Module):
         self._packed = None
         if w.is_cuda and w.dtype == torch.bfloat16 and self.fc1.in_features == 128 and self.fc1.out_features == 256 \
                 and self.raw_width == 72:
-            self._packed = pack_mlp_weights([self.fc1.weight, self.fc2.weight, self.fc3.weight, w[:80]],
-                                            [self.fc1.bias, self.fc2.bias, self.fc3.bias, b[:80]])
+            ws = [self.fc1.weight, self.fc2.weight, self.fc3.weight, w[:80]]
+            bs = [self.fc1.bias, self.fc2.bias, self.fc3.bias, b[:80]]
+            self._packed = pack_mlp_weights(ws, bs)
+            self._image32 = pack_mlp_weights(ws, bs, split_halves=False)[0]
 
     def fused_kernel_ok(self, planes: torch.Tensor) -> bool:
         """the hand-written tcgen05 kernel covers exactly the Reversi shape in bf16 on a GPU"""
@@ -120,6 +123,11 @@ class PolicyValueMLP(nn.Module):
             hw, hb = self._head_full
             x = planes.reshape(B, -1)
             L = _lib.load()
+            if fused != "ldgsts" and getattr(self, "_image32", None) is not None:  # weights by cp.async.bulk (TMA)
+                _lib.check(L.bz_mlp_forward_image(_lib.dptr(x), _lib.dptr(self._image32), _lib.dptr(self.fc1.bias),
+                                                  _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.bias), _lib.dptr(hb),
+                                                  _lib.dptr(out), B, _lib.stream_ptr()), "bz_mlp_forward_image")
+                return out
             _lib.check(L.bz_mlp_forward(_lib.dptr(x), _lib.dptr(self.fc1.weight), _lib.dptr(self.fc1.bias),
                                         _lib.dptr(self.fc2.weight), _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.weight),
                                         _lib.dptr(self.fc3.bias), _lib.dptr(hw), _lib.dptr(hb), _lib.dptr(out), B,

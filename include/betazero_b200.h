@@ -313,6 +313,13 @@ int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const voi
                    const void *w3, const void *b3, const void *w_head, const void *b_head, void *out_bf16,
                    int64_t n, int in_features, int hidden, int head_rows, int out_stride, bz_stream_t stream);
 
+/* bz_mlp_forward with the weights streamed by cp.async.bulk (TMA) instead of 16-byte LDGSTS copies:
+ * weight_image32 = 14 units of 32 KB in (layer, K slab) order (layer 0: 2 slabs, layers 1-2: 4, head: 4
+ * with 80 rows), each unit = all 256 weight rows of one 64-column K slab in the K-major SWIZZLE_128B
+ * shared-memory layout (betazero_b200.net.pack_mlp_weights(..., split_halves=False)); biases bf16. */
+int bz_mlp_forward_image(const void *x_bf16, const void *weight_image32, const void *b1, const void *b2,
+                         const void *b3, const void *b_head, void *out_bf16, int64_t n, bz_stream_t stream);
+
 /* The same network as a warp-specialised, software-pipelined kernel (MMA issuer / weight producer /
  * 16 epilogue warps; TMEM and activation double buffering, cp.async.bulk weight streaming).
  * weight_image: bz_mlp_weight_image_bytes() bytes = 24 units of 16 KB in consumption order

@@ -17,7 +17,8 @@ def _planes(B, seed):
     return torch.stack([(a == 1), (a == 2)], dim=1).reshape(B, 2, 8, 8).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("variant", [True, "v2"])  # True: bz_mlp_forward; "v2": pipelined bz_mlp_forward_packed
+# True: bz_mlp_forward_image (TMA weights); "ldgsts": bz_mlp_forward (raw weights); "v2": pipelined bz_mlp_forward_packed
+@pytest.mark.parametrize("variant", [True, "ldgsts", "v2"])
 @pytest.mark.parametrize("B", [1, 7, 128, 129, 1000, 4096])
 def test_fused_mlp_matches_torch_module(B, variant):
     from betazero_b200 import net
@@ -58,8 +59,8 @@ def test_fused_mlp_is_deterministic_and_row_independent():
     assert torch.equal(a, b)
     c = m.forward_raw(x[37:38].contiguous(), fused=True)
     assert torch.equal(c[0], a[37])  # a row's result does not depend on its batch
-    v2 = m.forward_raw(x, fused="v2")
-    assert torch.equal(a, v2)  # both kernels accumulate in the same order (K ascending, fp32 in TMEM)
+    for other in ("v2", "ldgsts"):
+        assert torch.equal(a, m.forward_raw(x, fused=other))  # same accumulation order (K ascending, fp32 in TMEM)
 
 
 def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
