@@ -27,7 +27,7 @@ constexpr int kSlabB = kHidden * 128;    // one K slab of B: 256 rows x 128 B
 constexpr int kSmemA = 4 * kSlabA;       // 64 KB
 constexpr int kSmemB = 4 * kSlabB;       // 128 KB
 constexpr int kSmemBias = kHidden * 4;   // 1 KB
-constexpr int kSmemTotal = kSmemA + kSmemB + kSmemBias + 64 + 1024;  // + barriers/tmem slot + alignment slack
+constexpr int kSmemTotal = kSmemA + kSmemB + kSmemBias + 128 + 1024;  // + barriers/tmem slot + alignment slack
 constexpr int kTmemCols = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
