@@ -169,7 +169,7 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
-            "net_backend": ("bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch"
+            "net_backend": ("bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch"
                             if getattr(args, "kernel_net", False) else "PyTorch/cuBLASLt GEMMs"),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
@@ -364,7 +364,7 @@ def alt_backend(torch, mcts, selfplay, net, args):
         ms = e0.elapsed_time(e1) / n
         sp.mcts.check_errors()
         return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms,
-                "net_backend": ("bz_mlp_forward (tcgen05, one launch) + programmatic dependent launch" if use_kernel
+                "net_backend": ("bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch" if use_kernel
                                 else "PyTorch/cuBLASLt GEMMs")}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
