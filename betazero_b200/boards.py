@@ -166,3 +166,8 @@ class TicTacToeBoard:
         x, o = self._wire()
         m = int(env.to_host_u16(env.ttt_legal_mask(x, o))[0])
         return [(i, j) for i in range(3) for j in range(3) if (m >> (i * 3 + j)) & 1]
+
+
+# names used in SURVEY.md section 8b for the drop-in classes
+GpuReversiBoard = ReversiBoard
+GpuTicTacToeBoard = TicTacToeBoard
