@@ -163,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": r2["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "positions_per_sec": r2["positions_per_sec"], "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -334,7 +334,7 @@ def run_b200(args):
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay_sample(
                 args.cpu_trees, S, args.net, args.hidden, args.cpu_seconds, None).items()
                 if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -450,8 +450,27 @@ def side_measurements(torch, env, hbm_peak):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this run, written to the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Libraries (NCCL's version banner, torchrun notices, ...) print to fd 1; the contract is exactly one JSON
+    # line on stdout, so fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
