@@ -166,11 +166,17 @@ def run_reference(args):
     emit(line)
 
 
+def kernel_net_label(games):
+    if games <= 74 * 128:
+        return ("bz_mlp_forward_pair (tcgen05 cta_group::2, weights resident in shared memory, one launch) "
+                "+ programmatic dependent launch")
+    return "bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch"
+
+
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
-            "net_backend": ("bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch"
-                            if getattr(args, "kernel_net", False) else "PyTorch/cuBLASLt GEMMs"),
+            "net_backend": (kernel_net_label(args.games) if getattr(args, "kernel_net", False) else "PyTorch/cuBLASLt GEMMs"),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -347,7 +353,7 @@ def alt_backend(torch, mcts, selfplay, net, args):
 
     use_kernel = not getattr(args, "kernel_net", False)
     try:
-        ev = mcts.FusedNetEvaluator(net, use_kernel=True if use_kernel else False)
+        ev = mcts.FusedNetEvaluator(net, use_kernel=None if use_kernel else False)
         bzlib.set_pdl(use_kernel)
         sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll)
         sp.prepare()
@@ -364,8 +370,7 @@ def alt_backend(torch, mcts, selfplay, net, args):
         ms = e0.elapsed_time(e1) / n
         sp.mcts.check_errors()
         return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms,
-                "net_backend": ("bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch" if use_kernel
-                                else "PyTorch/cuBLASLt GEMMs")}
+                "net_backend": kernel_net_label(args.games) if use_kernel else "PyTorch/cuBLASLt GEMMs"}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
     finally:

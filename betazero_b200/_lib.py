@@ -79,6 +79,8 @@ SIGNATURES = {
     "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_forward": [ptr] * 10 + [_I64, _INT, _INT, _INT, _INT, ptr],
     "bz_mlp_forward_image": [ptr] * 7 + [_I64, ptr],
+    "bz_mlp_forward_pair": [ptr, ptr, ptr, _I64, ptr],
+    "bz_mlp_pair_image_bytes": [],
     "bz_mlp_forward_packed": [ptr, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_weight_image_bytes": [],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],

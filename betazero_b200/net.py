@@ -44,6 +44,32 @@ def pack_mlp_weights(weights, biases, split_halves: bool = True):
     return image, bias
 
 
+def _swizzled_slabs(W: torch.Tensor) -> torch.Tensor:
+    """[rows, K] bf16 -> uint8 [K/64 slabs, rows * 128 B]: K-major SWIZZLE_128B (16-byte chunk j of row r
+    at chunk j ^ (r & 7) of its 128-byte row), the shared-memory image of a UMMA operand."""
+    rows, K = W.shape
+    v = W.contiguous().view(rows, K // 64, 8, 8).permute(1, 0, 2, 3).contiguous()  # [s, r, j, e]
+    r = torch.arange(rows, device=W.device)[:, None]
+    j = torch.arange(8, device=W.device)[None, :]
+    src = (j ^ (r & 7))[None, :, :, None].expand(K // 64, rows, 8, 8)
+    return torch.gather(v, 2, src).reshape(K // 64, rows * 64).view(torch.uint8)
+
+
+def pack_mlp_pair_image(weights, biases) -> torch.Tensor:
+    """Weight image of ``bz_mlp_forward_pair``: uint8 [2, 187712]; rank r of a CTA pair holds output rows
+    r*N/2 .. (r+1)*N/2 of every layer (N = 256, 256, 256, 80), layer after layer, each layer as K/64 slabs,
+    then all 848 biases as float32."""
+    bias = torch.cat([b.float().reshape(-1) for b in biases]).contiguous().view(torch.uint8)
+    ranks = []
+    for r in range(2):
+        parts = []
+        for W in weights:
+            h = W.shape[0] // 2
+            parts.append(_swizzled_slabs(W[r * h:(r + 1) * h]).reshape(-1))
+        ranks.append(torch.cat(parts + [bias]))
+    return torch.stack(ranks).contiguous()
+
+
 class PolicyValueMLP(nn.Module):
     """in -> H -> H -> H -> (A logits, 1 value): TicTacToeNet (neural_networks.py:4-30) + value head."""
 
@@ -86,6 +112,7 @@ class PolicyValueMLP(nn.Module):
             bs = [self.fc1.bias, self.fc2.bias, self.fc3.bias, b[:80]]
             self._packed = pack_mlp_weights(ws, bs)
             self._image32 = pack_mlp_weights(ws, bs, split_halves=False)[0]
+            self._image_pair = pack_mlp_pair_image(ws, bs)
 
     def fused_kernel_ok(self, planes: torch.Tensor) -> bool:
         """the hand-written tcgen05 kernel covers exactly the Reversi shape in bf16 on a GPU"""
@@ -98,17 +125,23 @@ class PolicyValueMLP(nn.Module):
         """[B, raw_width]: policy logits in columns 0..A-1, PRE-tanh value in column A.
 
         ``fused=False``: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.
-        ``fused=True``: the hand-written single-launch tcgen05 kernel (``bz_mlp_forward``);
+        ``fused="pair"``: the single-launch tcgen05 kernel on CTA pairs (``bz_mlp_forward_pair``: cta_group::2
+        MMAs, each CTA keeps half of every weight matrix resident in shared memory);
+        ``fused=True``: the one-CTA-per-128-rows kernel with TMA weight streaming (``bz_mlp_forward_image``),
+        ``"ldgsts"`` the same kernel on the raw nn.Linear weights (``bz_mlp_forward``);
         ``fused="v2"``: its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).
-        ``fused=None`` (default) picks the kernel for the supported shape when the batch fits one wave
-        of 128-row CTAs (<= 18944 rows), else the library GEMMs.  Measured on B200 at 4096 rows, per
-        MCTS iteration: library 22.4 us, kernel 22.6 us, kernel + programmatic dependent launch
-        (``_lib.set_pdl``) 20.3 us, v2 24.7 / 23.5 us (profiles/README.md)."""
+        ``fused=None`` (default) picks, for the supported shape, the pair kernel while one wave of CTA pairs
+        covers the batch (<= 74 x 128 rows), the one-CTA kernel up to 148 x 128 rows, else the library GEMMs.
+        All kernels give bit-identical outputs.  Measured on B200 at 4096 rows, per MCTS iteration with
+        programmatic dependent launch: library 22.3 us, one-CTA kernel 19.0 us, pair kernel 15.9 us
+        (profiles/README.md)."""
         if self._head is None:
             self.prepare_inference()
         B = planes.shape[0]
-        if fused is None:  # auto: the single-launch kernel while one wave of 128-row CTAs covers the batch
+        if fused is None:  # auto: a single-launch kernel while one wave of CTAs covers the batch
             fused = self.fused_kernel_ok(planes) and B <= 148 * 128
+            if fused and B <= 74 * 128:
+                fused = "pair"
         if fused:
             from . import _lib
 
@@ -123,6 +156,10 @@ class PolicyValueMLP(nn.Module):
             hw, hb = self._head_full
             x = planes.reshape(B, -1)
             L = _lib.load()
+            if fused == "pair" and getattr(self, "_image_pair", None) is not None:  # CTA pairs, weights resident
+                _lib.check(L.bz_mlp_forward_pair(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B,
+                                                 _lib.stream_ptr()), "bz_mlp_forward_pair")
+                return out
             if fused != "ldgsts" and getattr(self, "_image32", None) is not None:  # weights by cp.async.bulk (TMA)
                 _lib.check(L.bz_mlp_forward_image(_lib.dptr(x), _lib.dptr(self._image32), _lib.dptr(self.fc1.bias),
                                                   _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.bias), _lib.dptr(hb),

@@ -320,6 +320,18 @@ int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const voi
 int bz_mlp_forward_image(const void *x_bf16, const void *weight_image32, const void *b1, const void *b2,
                          const void *b3, const void *b_head, void *out_bf16, int64_t n, bz_stream_t stream);
 
+/* The same network on CTA pairs (clusters of 2, tcgen05.mma.cta_group::2): each pair owns 128 rows, each
+ * CTA 64 of them and HALF of every weight matrix (the B operand of a pair MMA is split by output row), so
+ * the whole net (180 KB per CTA) is resident in shared memory after five bulk copies issued at kernel
+ * start.  weight_image_pair: bz_mlp_pair_image_bytes() bytes = [2 ranks][W1 half: 2 K slabs x 128 rows |
+ * W2 half: 4 x 128 | W3 half: 4 x 128 | head half: 4 x 40 rows, 128 B per row, K-major SWIZZLE_128B |
+ * biases float32 [256 + 256 + 256 + 80]] (betazero_b200.net.pack_mlp_pair_image builds it; rank r holds
+ * rows r*128.. of the hidden layers and rows r*40.. of the 80-row head; both ranks carry all biases).
+ * x / out as in bz_mlp_forward; results are bit-identical to it. */
+int bz_mlp_forward_pair(const void *x_bf16, const void *weight_image_pair, void *out_bf16, int64_t n,
+                        bz_stream_t stream);
+int64_t bz_mlp_pair_image_bytes(void);
+
 /* The same network as a warp-specialised, software-pipelined kernel (MMA issuer / weight producer /
  * 16 epilogue warps; TMEM and activation double buffering, cp.async.bulk weight streaming).
  * weight_image: bz_mlp_weight_image_bytes() bytes = 24 units of 16 KB in consumption order

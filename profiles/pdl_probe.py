@@ -21,7 +21,8 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 ref = None
-for name, use_kernel, pdl in (("library GEMMs", False, False), ("library GEMMs + PDL attribute on the step kernel", False, True), ("fused MLP kernel", True, False), ("fused MLP kernel + PDL", True, True)):
+for name, use_kernel, pdl in (("library GEMMs", False, False), ("library GEMMs + PDL attribute on the step kernel", False, True), ("fused MLP kernel", True, False), ("fused MLP kernel + PDL", True, True),
+                              ("pair MLP kernel", "pair", False), ("pair MLP kernel + PDL", "pair", True)):
     _lib.set_pdl(pdl)
     pools = mcts.TreePools(B, S)
     s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=use_kernel), graph_unroll=16)
@@ -34,7 +35,7 @@ for name, use_kernel, pdl in (("library GEMMs", False, False), ("library GEMMs +
     s.check_errors()
     if name == "fused MLP kernel":
         ref = cnt
-    elif name.startswith("fused MLP kernel +"):
+    elif "MLP kernel" in name:
         print("   PDL result identical to non-PDL:", bool(torch.equal(ref, cnt)))
     print(f"{name}: {ms:.2f} ms per search = {ms / S * 1e3:.2f} us/iteration, visits ok: {bool((cnt.sum(1) == S - 1).all())}")
 _lib.set_pdl(False)
