@@ -354,7 +354,6 @@ def alt_backend(torch, mcts, selfplay, net, args):
     use_kernel = not getattr(args, "kernel_net", False)
     try:
         ev = mcts.FusedNetEvaluator(net, use_kernel=None if use_kernel else False)
-        bzlib.set_pdl(use_kernel)
         sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll)
         sp.prepare()
         for _ in range(3):

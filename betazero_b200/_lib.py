@@ -140,7 +140,19 @@ def dptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_pdl_state = None  # last value given to bz_set_pdl (None: not set yet, the library default is off)
+
+
 def set_pdl(enable: bool) -> bool:
     """Process-wide switch for programmatic dependent launch between the tree step kernel and the
-    fused MLP kernel (bz_set_pdl).  Returns the previous setting."""
-    return bool(load().bz_set_pdl(1 if enable else 0))
+    fused MLP kernel (bz_set_pdl).  Returns the previous setting.  The launch attribute is only safe
+    when a step kernel never directly follows another step kernel in the stream (its prologue reads
+    tree state before it waits for the previous grid), so ``BatchedMCTS`` sets it before every launch
+    from its evaluator's ``pdl`` attribute; the cached value makes the repeated call free."""
+    global _pdl_state
+    enable = bool(enable)
+    if _pdl_state is enable:
+        return enable
+    prev = bool(load().bz_set_pdl(1 if enable else 0))
+    _pdl_state = enable
+    return prev

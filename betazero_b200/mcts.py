@@ -80,8 +80,8 @@ class TreePools:
         s = BzTreePools()
         s.game, s.board_size, s.n_trees, s.n_actions = game, (self.board_size if game == GAME_REVERSI else 8), self.n_trees, self.n_actions
         s.arena_units, s.max_depth, s.c_puct, s.prior_mode = self.arena_units, self.max_depth, self.c_puct, self.prior_mode
-        if group_lanes not in (0, 8, 32):
-            raise ValueError("group_lanes must be 0 (auto), 8 or 32")
+        if group_lanes not in (0, 8, 16, 32):
+            raise ValueError("group_lanes must be 0 (auto), 8, 16 or 32")
         self.group_lanes = int(group_lanes)
         s.eval_stride, s.group_lanes = self.eval_stride, self.group_lanes
         for name, _ in BzTreePools._fields_[BzTreePools.N_SCALARS:]:
@@ -186,8 +186,6 @@ class FusedNetEvaluator:
         self.value = torch.zeros(1, dtype=torch.float32, device=pools.device)  # unused in this mode
         pools.set_prior_mode(PRIOR_LOGITS_BF16, self.stride)
         self.refresh()
-        if self.pdl:
-            _lib.set_pdl(True)
         return self.out, self.value
 
     def refresh(self) -> None:
@@ -227,6 +225,9 @@ class BatchedMCTS:
         self._graph = None
         self._L = _lib.load()
         self.launches = 0  # kernels of libbetazero_b200 launched (bench.py's gpu_launches)
+        # Programmatic dependent launch is a property of THIS search's kernel sequence: only an evaluator that puts a
+        # kernel between two step kernels (FusedNetEvaluator) may ask for it; applied before every launch / capture.
+        self._pdl = bool(getattr(evaluator, "pdl", False))
 
     # -- single kernels ------------------------------------------------------------------------
     def reset(self, root_me: torch.Tensor, root_opp: torch.Tensor) -> None:
@@ -237,19 +238,23 @@ class BatchedMCTS:
         self.launches += 1
 
     def select(self) -> None:
+        _lib.set_pdl(self._pdl)
         _lib.check(self._L.bz_mcts_select(self.pools._ref, _lib.stream_ptr()), "bz_mcts_select")
         self.launches += 1
 
     def evaluate(self) -> None:
+        _lib.set_pdl(self._pdl)
         self.evaluator(self.pools)
 
     def expand_backup(self) -> None:
+        _lib.set_pdl(self._pdl)
         _lib.check(self._L.bz_mcts_expand_backup(self.pools._ref, _lib.dptr(self.prior_w), _lib.dptr(self.value),
                                                  _lib.stream_ptr()), "bz_mcts_expand_backup")
         self.launches += 1
 
     def step(self) -> None:
         if self.fused:
+            _lib.set_pdl(self._pdl)
             _lib.check(self._L.bz_mcts_step(self.pools._ref, _lib.dptr(self.prior_w), _lib.dptr(self.value),
                                             _lib.stream_ptr()), "bz_mcts_step")
             self.launches += 1

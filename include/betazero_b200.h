@@ -172,7 +172,7 @@ typedef struct bz_tree_pools {
     float c_puct;
     int32_t prior_mode;  /* BZ_PRIOR_WEIGHTS / BZ_PRIOR_LOGITS_BF16 */
     int32_t eval_stride; /* row stride (elements) of eval_out in logits mode (>= n_actions + 1) */
-    int32_t group_lanes; /* lanes that own one tree: 32 (warp per tree), 8 (4 trees per warp), 0 = choose by n_trees */
+    int32_t group_lanes; /* lanes that own one tree: 32 (warp per tree), 16, 8 (4 trees per warp), 0 = choose by n_trees */
     /* per tree [n_trees] */
     uint64_t *root_me, *root_opp;
     uint32_t *root_meta;  /* like an edge's meta, for the (virtual) edge into the root */

@@ -23,9 +23,8 @@ def timed(fn, n=5):
 ref = None
 for name, use_kernel, pdl in (("library GEMMs", False, False), ("library GEMMs + PDL attribute on the step kernel", False, True), ("fused MLP kernel", True, False), ("fused MLP kernel + PDL", True, True),
                               ("pair MLP kernel", "pair", False), ("pair MLP kernel + PDL", "pair", True)):
-    _lib.set_pdl(pdl)
     pools = mcts.TreePools(B, S)
-    s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=use_kernel), graph_unroll=16)
+    s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=use_kernel, pdl=pdl), graph_unroll=16)
     s.prepare()
     def one():
         s.reset(me, opp)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # north_star: Q values and policy targets within 1e-5 relative
 
 
-GROUPS = [32, 8]  # lanes per tree: warp-per-tree (small batches) and 4-trees-per-warp (large batches)
+GROUPS = [32, 16, 8]  # lanes per tree: warp-per-tree (small batches), 2 and 4 trees per warp (larger batches)
 
 
 def _search(me_h, opp_h, n_sims, salt, game=0, size=8, c_puct=1.25, group_lanes=0, **kw):

@@ -86,7 +86,7 @@ def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
 
 
 def test_programmatic_dependent_launch_changes_nothing_but_time():
-    """bz_set_pdl: the step kernel and the fused MLP kernel overlap prologue/tail; results identical"""
+    """FusedNetEvaluator(pdl=...): the step kernel and the fused MLP kernel overlap prologue/tail; results identical"""
     from betazero_b200 import _lib, env, mcts, net
     from oracle import pyoracle as po
 
@@ -96,11 +96,44 @@ def test_programmatic_dependent_launch_changes_nothing_but_time():
     out = []
     try:
         for pdl in (False, True):
-            assert _lib.set_pdl(pdl) in (True, False)
             pools = mcts.TreePools(B, n_sims)
-            s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=True), use_graph=True, graph_unroll=8)
+            s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=True, pdl=pdl), use_graph=True, graph_unroll=8)
             cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
             out.append((cnt.clone(), q.clone()))
     finally:
         _lib.set_pdl(False)
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_pdl_flag_does_not_leak_into_searches_without_a_kernel_between_steps():
+    """A search whose evaluator launches nothing between two step kernels must not inherit the launch
+    attribute from an earlier FusedNetEvaluator search (adjacent step kernels would overlap)."""
+    from betazero_b200 import _lib, env, mcts, net
+    from oracle import pyoracle as po
+
+    B, n_sims = 256, 64
+    me_h, opp_h = po.playout_boards(B, seed=5)
+    me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
+    model = net.make_net("mlp", seed=7)
+    s0 = mcts.BatchedMCTS(mcts.TreePools(B, n_sims), mcts.FusedNetEvaluator(model), graph_unroll=8)
+    s0.search(me, opp, n_sims)
+    assert _lib._pdl_state is True
+
+    class Static:  # fixed logits, no kernel of its own
+        prior_mode, stride = mcts.PRIOR_LOGITS_BF16, 72
+
+        def bind(self, pools):
+            g = torch.Generator(device="cuda").manual_seed(3)
+            self.out = torch.randn((B, 72), device="cuda", generator=g).to(torch.bfloat16)
+            return self.out, torch.zeros(1, device="cuda")
+
+        def __call__(self, pools):
+            pass
+
+    res = []
+    for graph in (True, False):
+        s1 = mcts.BatchedMCTS(mcts.TreePools(B, n_sims), Static(), use_graph=graph, graph_unroll=8)
+        res.append(s1.search(me, opp, n_sims)[0].clone())
+        assert _lib._pdl_state is False
+    assert torch.equal(res[0], res[1])
+    _lib.set_pdl(False)
