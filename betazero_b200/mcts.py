@@ -186,6 +186,11 @@ class FusedNetEvaluator:
         self.value = torch.zeros(1, dtype=torch.float32, device=pools.device)  # unused in this mode
         pools.set_prior_mode(PRIOR_LOGITS_BF16, self.stride)
         self.refresh()
+        # 1 when the forward is one kernel of libbetazero_b200 (bench.py's gpu_launches), 0 for library GEMMs
+        k = self.use_kernel
+        if k is None:
+            k = hasattr(self.net, "fused_kernel_ok") and self.net.fused_kernel_ok(pools.leaf_planes) and B <= 148 * 128
+        self.own_launches = 1 if k else 0
         return self.out, self.value
 
     def refresh(self) -> None:
@@ -245,6 +250,7 @@ class BatchedMCTS:
     def evaluate(self) -> None:
         _lib.set_pdl(self._pdl)
         self.evaluator(self.pools)
+        self.launches += getattr(self.evaluator, "own_launches", 0)  # kernels of this library the evaluator launched
 
     def expand_backup(self) -> None:
         _lib.set_pdl(self._pdl)
