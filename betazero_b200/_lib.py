@@ -22,14 +22,14 @@ class BzTreePools(C.Structure):
     _fields_ = [
         ("game", C.c_int32), ("board_size", C.c_int32), ("n_trees", C.c_int32), ("n_actions", C.c_int32),
         ("arena_units", C.c_int32), ("max_depth", C.c_int32), ("c_puct", C.c_float), ("prior_mode", C.c_int32),
-        ("eval_stride", C.c_int32), ("group_lanes", C.c_int32),
+        ("eval_stride", C.c_int32), ("group_lanes", C.c_int32), ("n_leaves", C.c_int32),
         ("root_me", ptr), ("root_opp", ptr), ("root_meta", ptr), ("arena_used", ptr), ("edge_count", ptr),
         ("sim_count", ptr), ("depth_sum", ptr), ("error", ptr),
         ("arena", ptr),
         ("path", ptr), ("path_len", ptr), ("leaf_parent", ptr), ("leaf_me", ptr), ("leaf_opp", ptr),
         ("leaf_mask", ptr), ("leaf_status", ptr), ("leaf_action", ptr), ("leaf_value", ptr), ("leaf_planes", ptr),
     ]
-    N_SCALARS = 10
+    N_SCALARS = 11
 
 
 class BzSelfplayState(C.Structure):

@@ -38,7 +38,8 @@ class TreePools:
 
     def __init__(self, n_trees: int, sims_cap: int, game: int = GAME_REVERSI, board_size: int = 8,
                  c_puct: float = 1.25, arena_units: int | None = None, max_depth: int | None = None,
-                 prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, group_lanes: int = 0, device="cuda"):
+                 prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, group_lanes: int = 0, n_leaves: int = 1,
+                 device="cuda"):
         if game not in (GAME_REVERSI, GAME_TTT):
             raise ValueError("game must be GAME_REVERSI or GAME_TTT")
         self.game, self.board_size = game, (3 if game == GAME_TTT else board_size)
@@ -54,7 +55,14 @@ class TreePools:
         self.max_depth = int(max_depth or (16 if game == GAME_TTT else 128))
         self.prior_mode, self.eval_stride = int(prior_mode), int(eval_stride)
         self.device = torch.device(device)
+        # leaves per tree and iteration: 1 = the sequential parity definition; K > 1 = K descents with virtual loss
+        # (oracle/mcts_ref.py MCTS.select_vl).  Pending-leaf arrays are slot-major: row = slot * n_trees + tree.
+        if not 1 <= int(n_leaves) <= 8:
+            raise ValueError("n_leaves must be in 1..8")
+        self.n_leaves = int(n_leaves)
+        self.n_rows = self.n_trees * self.n_leaves
         B = max(self.n_trees, 1)
+        R = max(self.n_rows, 1)
         dev = self.device
 
         def e(n, dt):
@@ -67,16 +75,16 @@ class TreePools:
         self.edge_count, self.sim_count = torch.zeros(B, dtype=torch.int32, device=dev), e(B, torch.int32)
         self.depth_sum, self.error = e(B, torch.int32), torch.zeros(B, dtype=torch.int32, device=dev)
         self.arena = e(B * self.arena_units * 8, torch.int32)
-        self.path, self.path_len = e(B * self.max_depth * 4, torch.int32), torch.zeros(B, dtype=torch.int32, device=dev)
-        self.leaf_parent = e(B, torch.int32)
-        self.leaf_me, self.leaf_opp, self.leaf_mask = e(B, torch.int64), e(B, torch.int64), e(B, torch.int64)
-        self.leaf_status = torch.full((B,), LEAF_ERROR, dtype=torch.uint8, device=dev)
-        self.leaf_action = e(B, torch.uint8)
-        self.leaf_value = e(B, torch.float32)
+        self.path, self.path_len = e(R * self.max_depth * 4, torch.int32), torch.zeros(R, dtype=torch.int32, device=dev)
+        self.leaf_parent = e(R, torch.int32)
+        self.leaf_me, self.leaf_opp, self.leaf_mask = e(R, torch.int64), e(R, torch.int64), e(R, torch.int64)
+        self.leaf_status = torch.full((R,), LEAF_ERROR, dtype=torch.uint8, device=dev)
+        self.leaf_action = e(R, torch.uint8)
+        self.leaf_value = e(R, torch.float32)
         if game == GAME_TTT:
-            self.leaf_planes = torch.zeros((B, 9), dtype=torch.bfloat16, device=dev)
+            self.leaf_planes = torch.zeros((R, 9), dtype=torch.bfloat16, device=dev)
         else:
-            self.leaf_planes = torch.zeros((B, 2, 8, 8), dtype=torch.bfloat16, device=dev)
+            self.leaf_planes = torch.zeros((R, 2, 8, 8), dtype=torch.bfloat16, device=dev)
         s = BzTreePools()
         s.game, s.board_size, s.n_trees, s.n_actions = game, (self.board_size if game == GAME_REVERSI else 8), self.n_trees, self.n_actions
         s.arena_units, s.max_depth, s.c_puct, s.prior_mode = self.arena_units, self.max_depth, self.c_puct, self.prior_mode
@@ -84,6 +92,7 @@ class TreePools:
             raise ValueError("group_lanes must be 0 (auto), 8, 16 or 32")
         self.group_lanes = int(group_lanes)
         s.eval_stride, s.group_lanes = self.eval_stride, self.group_lanes
+        s.n_leaves = self.n_leaves
         for name, _ in BzTreePools._fields_[BzTreePools.N_SCALARS:]:
             setattr(s, name, getattr(self, name).data_ptr())
         self.c_struct = s
@@ -109,7 +118,7 @@ class HashEvaluator:
         self.salt = int(salt)
 
     def bind(self, pools: "TreePools"):
-        B, A = max(pools.n_trees, 1), pools.n_actions
+        B, A = max(pools.n_rows, 1), pools.n_actions  # one row per pending leaf
         self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
         self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
         return self.out, self.value
@@ -117,7 +126,7 @@ class HashEvaluator:
     def __call__(self, pools: "TreePools") -> None:
         L = _lib.load()
         _lib.check(L.bz_hash_eval(_lib.dptr(pools.leaf_me), _lib.dptr(pools.leaf_opp), self.salt, pools.n_actions,
-                                  _lib.dptr(self.out), _lib.dptr(self.value), pools.n_trees, _lib.stream_ptr()),
+                                  _lib.dptr(self.out), _lib.dptr(self.value), pools.n_rows, _lib.stream_ptr()),
                    "bz_hash_eval")
 
 
@@ -127,7 +136,7 @@ class WeightsEvaluator:
     prior_mode = PRIOR_WEIGHTS
 
     def bind(self, pools: "TreePools"):
-        B, A = max(pools.n_trees, 1), pools.n_actions
+        B, A = max(pools.n_rows, 1), pools.n_actions  # one row per pending leaf
         self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
         self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
         return self.out, self.value
@@ -148,7 +157,7 @@ class NetEvaluator:
         self.net = net
 
     def bind(self, pools: "TreePools"):
-        B, A = max(pools.n_trees, 1), pools.n_actions
+        B, A = max(pools.n_rows, 1), pools.n_actions  # one row per pending leaf
         self.out = torch.zeros((B, A), dtype=torch.float32, device=pools.device)
         self.value = torch.zeros(B, dtype=torch.float32, device=pools.device)
         return self.out, self.value
@@ -180,7 +189,7 @@ class FusedNetEvaluator:
         self.pdl = (use_kernel is not False) if pdl is None else bool(pdl)
 
     def bind(self, pools: "TreePools"):
-        B = max(pools.n_trees, 1)
+        B = max(pools.n_rows, 1)  # one row per pending leaf
         self.stride = int(self.net.raw_width)
         self.out = torch.zeros((B, self.stride), dtype=torch.bfloat16, device=pools.device)
         self.value = torch.zeros(1, dtype=torch.float32, device=pools.device)  # unused in this mode
@@ -300,15 +309,18 @@ class BatchedMCTS:
         self._graph = g
 
     def run(self, n_sims: int) -> None:
-        """n_sims iterations on the current trees (after :meth:`reset`)."""
+        """n_sims simulations on the current trees (after :meth:`reset`): n_sims / n_leaves iterations."""
         if n_sims <= 0:
             return
         if n_sims > self.pools.sims_cap:
             raise ValueError(f"n_sims {n_sims} exceeds the pools' sims_cap {self.pools.sims_cap}")
+        K = self.pools.n_leaves
+        if n_sims % K:
+            raise ValueError(f"n_sims {n_sims} is not a multiple of the pools' n_leaves {K}")
         if self.pools.n_trees == 0:
             return
         self.select()
-        inner = n_sims - 1
+        inner = n_sims // K - 1
         if self.dirichlet_alpha > 0 and inner > 0:
             # iteration 1 expands the root; perturb its priors before the second descent
             self.evaluate()
@@ -347,7 +359,7 @@ class BatchedMCTS:
 
     def search(self, root_me: torch.Tensor, root_opp: torch.Tensor, n_sims: int, check: bool = True):
         """Fresh search from the given roots.  Returns (visit_counts, pi, q) device tensors."""
-        if self.use_graph and self._graph is None and n_sims - 1 >= self.unroll:
+        if self.use_graph and self._graph is None and n_sims // self.pools.n_leaves - 1 >= self.unroll:
             self.prepare()
         self.reset(root_me, root_opp)
         self.run(n_sims)

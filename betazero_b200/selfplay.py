@@ -25,11 +25,12 @@ class BatchedSelfPlay:
     def __init__(self, n_games: int, n_sims: int, evaluator, board_size: int = 8, c_puct: float = 1.25,
                  temp_plies: int = 0, seed: int = 0, replay_cap: int | None = None, rank: int = 0, world: int = 1,
                  arena_units: int | None = None, use_graph: bool = True, graph_unroll: int = 16,
-                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, device="cuda"):
+                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, n_leaves: int = 1, device="cuda"):
         self.n_games, self.n_sims, self.board_size = int(n_games), int(n_sims), int(board_size)
         self.rank, self.world = int(rank), int(world)
         self.device = torch.device(device)
-        self.pools = TreePools(n_games, n_sims, board_size=board_size, c_puct=c_puct, arena_units=arena_units, device=device)
+        self.pools = TreePools(n_games, n_sims, board_size=board_size, c_puct=c_puct, arena_units=arena_units,
+                               n_leaves=n_leaves, device=device)
         self.mcts = BatchedMCTS(self.pools, evaluator, use_graph=use_graph, graph_unroll=graph_unroll,
                                 dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps,
                                 noise_seed=seed * 7919 + rank)

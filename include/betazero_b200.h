@@ -32,7 +32,7 @@ extern "C" {
 #define BZ_OK 0
 #define BZ_ERR_ARG (-1)
 #define BZ_ERR_UNALIGNED (-2)
-#define BZ_ABI_VERSION 1
+#define BZ_ABI_VERSION 2
 
 #define BZ_REVERSI_ACTIONS 65
 #define BZ_TTT_ACTIONS 9
@@ -148,6 +148,8 @@ int bz_ttt_terminal(const uint16_t *x, const uint16_t *o, uint8_t *over, int8_t 
 #define BZ_MAX_ARENA_UNITS 0x7FFF0 /* 8-word units per tree (16.7 MB) */
 #define BZ_MAX_NODE_UNITS 18       /* worst case: 33 edges -> 8 + 132 words -> 18 units */
 
+#define BZ_MAX_LEAVES 8 /* pools.n_leaves */
+
 /* leaf_status values */
 #define BZ_LEAF_EVAL 0     /* needs the evaluator's output */
 #define BZ_LEAF_TERMINAL 1 /* game over at the leaf: value known, evaluator output ignored */
@@ -173,6 +175,11 @@ typedef struct bz_tree_pools {
     int32_t prior_mode;  /* BZ_PRIOR_WEIGHTS / BZ_PRIOR_LOGITS_BF16 */
     int32_t eval_stride; /* row stride (elements) of eval_out in logits mode (>= n_actions + 1) */
     int32_t group_lanes; /* lanes that own one tree: 32 (warp per tree), 16, 8 (4 trees per warp), 0 = choose by n_trees */
+    int32_t n_leaves;    /* 0 / 1: one leaf per tree and iteration (the bit-exact parity definition).  K in 2..BZ_MAX_LEAVES:
+                            K descents per tree and iteration with VIRTUAL LOSS (a descent leaves N += 1, W -= 1 on its
+                            edges until its backup): the pending-leaf arrays below then hold K * n_trees entries, slot-major
+                            (entry slot * n_trees + tree), eval_out / value have K * n_trees rows, and an iteration counts
+                            K simulations.  Definition and oracle: oracle/mcts_ref.py MCTS.select_vl / expand_backup_vl. */
     /* per tree [n_trees] */
     uint64_t *root_me, *root_opp;
     uint32_t *root_meta;  /* like an edge's meta, for the (virtual) edge into the root */
@@ -184,15 +191,15 @@ typedef struct bz_tree_pools {
     /* the arenas: uint32 [n_trees * arena_units * 8] */
     uint32_t *arena;
     /* pending leaf, per tree */
-    uint32_t *path;        /* [n_trees * max_depth * 4] records {word index of N, n, N, W bits}, root first */
-    int32_t *path_len;     /* [n_trees] */
+    uint32_t *path;        /* [rows * max_depth * 4] records {word index of N, n, N, W bits}, root first; rows = n_trees * max(n_leaves, 1) */
+    int32_t *path_len;     /* [rows] (and so on for every leaf_* array) */
     int32_t *leaf_parent;  /* arena word index of the meta of the edge into the leaf (-1: the leaf is the root) */
     uint64_t *leaf_me, *leaf_opp;
     uint64_t *leaf_mask;   /* legal cells of the leaf's mover (0 with status EVAL = the mover must pass) */
     uint8_t *leaf_status;
     uint8_t *leaf_action;  /* action of the edge into the leaf */
     float *leaf_value;     /* terminal value for the leaf's mover */
-    void *leaf_planes;     /* bf16 [n_trees, 2, 8, 8] canonical planes of the leaf (K6); TTT: [n_trees, 9] */
+    void *leaf_planes;     /* bf16 [rows, 2, 8, 8] canonical planes of the leaf (K6); TTT: [rows, 9] */
 } bz_tree_pools;
 
 /* Empty every tree and set its root position (mover-relative). */

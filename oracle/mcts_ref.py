@@ -142,11 +142,12 @@ class TicTacToeGame:
 
 # --------------------------------------------------------------------------- the search
 class _Node:
-    __slots__ = ("board", "player", "value", "actions", "P", "N", "W", "children")
+    __slots__ = ("board", "player", "value", "actions", "P", "N", "W", "children", "visits")
 
     def __init__(self, board, player, value):
         self.board, self.player, self.value = board, player, value  # value != None => terminal
         self.actions = None  # None until expanded
+        self.visits = 0  # descents that have entered the node (virtual-loss mode)
 
 
 class MCTS:
@@ -232,6 +233,84 @@ class MCTS:
             else:
                 w, v = None, F32(0)
             self.expand_backup(w, v)
+
+    # -- K leaves per iteration with virtual loss -------------------------------------------
+    # An iteration makes K descents one after the other (slots 0..K-1), evaluates the K leaves, then
+    # expands / backs them up in slot order.  A descent leaves a virtual loss on every edge it walks
+    # (N += 1, W = W - 1 in float32) so the following descents of the iteration are steered elsewhere.
+    # The visit count under the square root is the number of descents that have ENTERED the node
+    # before this one; for K = 1 that is exactly 1 + sum(child N) of select() above.  Two descents may
+    # end on the same unexpanded leaf: the first backup expands it, later ones only back up their value.
+    # Backup turns the virtual visit into a real one: W = (W + 1) + value (two float32 adds), N unchanged.
+    def select_vl(self, slot: int):
+        g = self.game
+        if not hasattr(self, "_vl"):
+            self._vl = {}
+        node, path = self.root, []
+        while True:
+            n_node = node.visits
+            node.visits += 1
+            if node.value is not None or node.actions is None:
+                break
+            sq = np.sqrt(F32(n_node))
+            best, best_score = 0, None
+            for i in range(len(node.actions)):
+                n = int(node.N[i])
+                q = node.W[i] / F32(n) if n > 0 else F32(0)
+                u = self.c_puct * node.P[i]
+                u = u * sq
+                u = u / F32(1 + n)
+                score = q + u
+                if best_score is None or score > best_score:
+                    best, best_score = i, score
+            path.append((node, best))
+            node.N[best] += 1
+            node.W[best] = node.W[best] - F32(1)
+            child = node.children[best]
+            if child is None:
+                nb, npl = g.next(node.board, node.player, node.actions[best])
+                child = _Node(nb, npl, g.terminal_value(nb, npl))
+                node.children[best] = child
+            node = child
+        self._vl[slot] = (path, node)
+        me, opp = g.wire(node.board, node.player)
+        return (1 if node.value is not None else 0), me, opp
+
+    def expand_backup_vl(self, slot: int, w, v):
+        path, leaf = self._vl.pop(slot)
+        if leaf.value is not None:
+            value = F32(leaf.value)
+        elif leaf.actions is not None:
+            value = F32(v)  # expanded by an earlier slot of this iteration
+        else:
+            acts = self.game.legal_actions(leaf.board, leaf.player)
+            s = F32(0)
+            for a in acts:
+                s = s + F32(w[a])
+            leaf.actions = acts
+            if s == 0:
+                leaf.P = np.array([F32(1) / F32(len(acts))] * len(acts), dtype=np.float32)
+            else:
+                leaf.P = np.array([F32(w[a]) / s for a in acts], dtype=np.float32)
+            leaf.N = np.zeros(len(acts), dtype=np.int32)
+            leaf.W = np.zeros(len(acts), dtype=np.float32)
+            leaf.children = [None] * len(acts)
+            value = F32(v)
+        for node, i in reversed(path):
+            value = -value
+            node.W[i] = (node.W[i] + F32(1)) + value
+        self.sum_depth += len(path)
+        self.n_sims += 1
+
+    def run_vl(self, n_sims: int, leaves: int):
+        assert n_sims % leaves == 0
+        for _ in range(n_sims // leaves):
+            evs = []
+            for j in range(leaves):
+                status, me, opp = self.select_vl(j)
+                evs.append(self.evaluator(me, opp) if status == 0 else (None, F32(0)))
+            for j in range(leaves):
+                self.expand_backup_vl(j, *evs[j])
 
     # -- results -----------------------------------------------------------------------
     def root_stats(self):

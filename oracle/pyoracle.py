@@ -91,6 +91,12 @@ def _declare(L):
     L.orc_mcts_batch_select.argtypes = [_pp, C.c_int64, _pu64, _pu64, _pu8, _pf]
     L.orc_mcts_batch_expand_backup.argtypes = [_pp, C.c_int64, _pf, _pf, C.c_int]
     L.orc_mcts_batch_root_counts.argtypes = [_pp, C.c_int64, _pi32, C.c_int]
+    L.orc_mcts_select_vl.argtypes = [C.c_void_p, C.c_int, _pu64, _pu64, _pint]
+    L.orc_mcts_expand_backup_vl.argtypes = [C.c_void_p, C.c_int, _pf, C.c_float]
+    L.orc_mcts_search_hash_vl.argtypes = [C.c_int, C.c_int, C.c_float, C.c_uint64, _pu64, _pu64, C.c_int64, C.c_int, C.c_int,
+                                          _pi32, _pf, _pf, _pi64]
+    L.orc_mcts_batch_select_vl.argtypes = [_pp, C.c_int64, C.c_int, _pu64, _pu64, _pu8, _pf]
+    L.orc_mcts_batch_expand_backup_vl.argtypes = [_pp, C.c_int64, C.c_int, _pf, _pf, C.c_int]
 
 
 def _ptr(a: np.ndarray, ty):
@@ -333,6 +339,16 @@ class OracleTree:
         w = _c(w if w is not None else np.zeros(self.n_actions), np.float32)
         lib().orc_mcts_expand_backup(self._t, _ptr(w, _pf), float(v))
 
+    # virtual-loss mode: several descents in flight (slots), oracle.c Part 2d
+    def select_vl(self, slot):
+        me, opp, d = C.c_uint64(), C.c_uint64(), C.c_int()
+        st = lib().orc_mcts_select_vl(self._t, int(slot), C.byref(me), C.byref(opp), C.byref(d))
+        return st, me.value, opp.value, d.value
+
+    def expand_backup_vl(self, slot, w, v):
+        w = _c(w if w is not None else np.zeros(self.n_actions), np.float32)
+        lib().orc_mcts_expand_backup_vl(self._t, int(slot), _ptr(w, _pf), float(v))
+
     def root_stats(self):
         cnt = np.zeros(self.n_actions, np.int32)
         W = np.zeros(self.n_actions, np.float32)
@@ -346,9 +362,10 @@ class OracleTree:
         return dict(nodes=int(c[0]), edges=int(c[1]), sum_depth=int(c[2]), sims=int(c[3]))
 
 
-def search_hash(me, opp, n_sims, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0):
+def search_hash(me, opp, n_sims, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0, leaves=1):
     """n_sims-iteration searches from every (me, opp) root with the hash evaluator, OpenMP over
-    trees.  Returns (counts int32[n,A], W f32[n,A], P f32[n,A], counters dict)."""
+    trees.  Returns (counts int32[n,A], W f32[n,A], P f32[n,A], counters dict).  ``leaves`` > 1: the
+    virtual-loss mode, ``leaves`` descents per iteration (n_sims must be a multiple)."""
     me, opp = _c(me, np.uint64), _c(opp, np.uint64)
     A = 9 if game == GAME_TTT else 65
     n = me.size
@@ -356,8 +373,14 @@ def search_hash(me, opp, n_sims, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0)
     W = np.zeros((n, A), np.float32)
     P = np.zeros((n, A), np.float32)
     c = np.zeros(4, np.int64)
-    lib().orc_mcts_search_hash(game, size, c_puct, salt, _ptr(me, _pu64), _ptr(opp, _pu64), n, n_sims,
-                               _ptr(cnt, _pi32), _ptr(W, _pf), _ptr(P, _pf), _ptr(c, _pi64))
+    if leaves > 1:
+        if n_sims % leaves:
+            raise ValueError("n_sims must be a multiple of leaves")
+        lib().orc_mcts_search_hash_vl(game, size, c_puct, salt, _ptr(me, _pu64), _ptr(opp, _pu64), n, n_sims, leaves,
+                                      _ptr(cnt, _pi32), _ptr(W, _pf), _ptr(P, _pf), _ptr(c, _pi64))
+    else:
+        lib().orc_mcts_search_hash(game, size, c_puct, salt, _ptr(me, _pu64), _ptr(opp, _pu64), n, n_sims,
+                                   _ptr(cnt, _pi32), _ptr(W, _pf), _ptr(P, _pf), _ptr(c, _pi64))
     return cnt, W, P, dict(nodes=int(c[0]), edges=int(c[1]), sum_depth=int(c[2]), sims=int(c[3]))
 
 
@@ -374,15 +397,16 @@ class OracleForest:
     """Many C trees stepped in lockstep (OpenMP over trees): the CPU baseline's counterpart of the
     GPU's BatchedMCTS, usable with any evaluator (e.g. the same PyTorch net on the CPU)."""
 
-    def __init__(self, n, game=GAME_REVERSI, size=8, c_puct=1.25):
-        self.n, self.game = int(n), game
+    def __init__(self, n, game=GAME_REVERSI, size=8, c_puct=1.25, leaves=1):
+        self.n, self.game, self.leaves = int(n), game, int(leaves)
         self.n_actions = 9 if game == GAME_TTT else 65
         self._trees = [lib().orc_mcts_new(game, size, c_puct) for _ in range(self.n)]
         self._arr = (C.c_void_p * self.n)(*self._trees)
-        self.leaf_me = np.zeros(self.n, np.uint64)
-        self.leaf_opp = np.zeros(self.n, np.uint64)
-        self.status = np.zeros(self.n, np.uint8)
-        self.planes = np.zeros((self.n, 2, 8, 8), np.float32)
+        rows = self.n * self.leaves  # leaf arrays are slot-major [leaves][n]
+        self.leaf_me = np.zeros(rows, np.uint64)
+        self.leaf_opp = np.zeros(rows, np.uint64)
+        self.status = np.zeros(rows, np.uint8)
+        self.planes = np.zeros((rows, 2, 8, 8), np.float32)
 
     def __del__(self):
         for t in getattr(self, "_trees", []):
@@ -394,12 +418,19 @@ class OracleForest:
         lib().orc_mcts_batch_reset_wire(self._arr, self.n, _ptr(me, _pu64), _ptr(opp, _pu64))
 
     def select(self):
-        lib().orc_mcts_batch_select(self._arr, self.n, _ptr(self.leaf_me, _pu64), _ptr(self.leaf_opp, _pu64),
-                                    _ptr(self.status, _pu8), _ptr(self.planes, _pf))
+        if self.leaves > 1:
+            lib().orc_mcts_batch_select_vl(self._arr, self.n, self.leaves, _ptr(self.leaf_me, _pu64),
+                                           _ptr(self.leaf_opp, _pu64), _ptr(self.status, _pu8), _ptr(self.planes, _pf))
+        else:
+            lib().orc_mcts_batch_select(self._arr, self.n, _ptr(self.leaf_me, _pu64), _ptr(self.leaf_opp, _pu64),
+                                        _ptr(self.status, _pu8), _ptr(self.planes, _pf))
 
     def expand_backup(self, w, v):
         w, v = _c(w, np.float32), _c(v, np.float32)
-        lib().orc_mcts_batch_expand_backup(self._arr, self.n, _ptr(w, _pf), _ptr(v, _pf), self.n_actions)
+        if self.leaves > 1:
+            lib().orc_mcts_batch_expand_backup_vl(self._arr, self.n, self.leaves, _ptr(w, _pf), _ptr(v, _pf), self.n_actions)
+        else:
+            lib().orc_mcts_batch_expand_backup(self._arr, self.n, _ptr(w, _pf), _ptr(v, _pf), self.n_actions)
 
     def root_counts(self):
         cnt = np.zeros((self.n, self.n_actions), np.int32)

@@ -376,3 +376,114 @@ def test_resnet_through_net_evaluator():
     live = po.terminal(me_h, opp_h)[0] == 0
     assert (cnt.cpu().numpy().sum(1)[live] == 23).all()
     assert torch.isfinite(pi).all() and torch.isfinite(q).all()
+
+
+# ---- K leaves per iteration with virtual loss (pools.n_leaves > 1) --------------------------------------------
+def _search_vl(me_h, opp_h, n_sims, salt, leaves, game=0, size=8, c_puct=1.25, group_lanes=0, **kw):
+    from betazero_b200 import env, mcts
+
+    pools = mcts.TreePools(len(me_h), n_sims, game=game, board_size=size, c_puct=c_puct, group_lanes=group_lanes,
+                           n_leaves=leaves)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(salt), **kw)
+    cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
+    return s, cnt.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy()
+
+
+@pytest.mark.parametrize("group", GROUPS)
+@pytest.mark.parametrize("leaves", [2, 4])
+def test_virtual_loss_reversi_vs_c_oracle(group, leaves):
+    """K descents per iteration with virtual loss (oracle.c Part 2d / mcts_ref.MCTS.select_vl): visit counts, W and P
+    of the root bit for bit, and the search counters (the collisions are part of the definition)"""
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(512, seed=15)
+    n_sims = 96
+    s, cnt, pi, q = _search_vl(me_h, opp_h, n_sims, 5, leaves, group_lanes=group)
+    r_cnt, r_W, r_P, ctr = po.search_hash(me_h, opp_h, n_sims, po.GAME_REVERSI, 8, 1.25, 5, leaves=leaves)
+    assert np.array_equal(cnt, r_cnt)
+    W, P = _root_W_P(s)
+    assert np.array_equal(W, r_W) and np.array_equal(P, r_P)
+    st = s.stats()
+    assert st["sims"] == ctr["sims"] == 512 * n_sims
+    assert st["edges"] == ctr["edges"]
+    assert abs(st["mean_depth"] - ctr["sum_depth"] / ctr["sims"]) < 1e-9
+    live = po.terminal(me_h, opp_h)[0] == 0
+    assert (cnt.sum(1)[live] == n_sims - leaves).all()  # the first iteration's descents all end on the unexpanded root
+
+
+@pytest.mark.parametrize("group", GROUPS)
+def test_virtual_loss_ttt_and_small_boards(group):
+    from betazero_b200 import mcts
+    from oracle import pyoracle as po
+
+    x = np.array([0, 0b000010000, 0b100000001, 0b000000111], dtype=np.uint64)
+    o = np.array([0, 0b000000001, 0b000010010, 0b011000000], dtype=np.uint64)
+    s, cnt, _, _ = _search_vl(x, o, 60, 3, 2, game=mcts.GAME_TTT, group_lanes=group)
+    r_cnt, r_W, _, _ = po.search_hash(x, o, 60, po.GAME_TTT, 3, 1.25, 3, leaves=2)
+    assert np.array_equal(cnt, r_cnt)
+    assert np.array_equal(_root_W_P(s)[0], r_W)
+    for size in (4, 6):
+        me_h, opp_h = po.playout_boards(64, seed=size, size=size)
+        s, cnt, _, _ = _search_vl(me_h, opp_h, 48, 1, 2, size=size, group_lanes=group)
+        r_cnt, _, _, _ = po.search_hash(me_h, opp_h, 48, po.GAME_REVERSI, size, 1.25, 1, leaves=2)
+        assert np.array_equal(cnt, r_cnt)
+
+
+def test_virtual_loss_800_sims_graph_path_vs_c_oracle():
+    """headline search length with 2 leaves per iteration (400 iterations), CUDA graph + fused step kernel"""
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(128, seed=6)
+    s, cnt, _, _ = _search_vl(me_h, opp_h, 800, 1, 2)
+    r_cnt, r_W, _, _ = po.search_hash(me_h, opp_h, 800, po.GAME_REVERSI, 8, 1.25, 1, leaves=2)
+    assert np.array_equal(cnt, r_cnt)
+    assert np.array_equal(_root_W_P(s)[0], r_W)
+    # plain (unfused, no graph) launches give the same trees
+    s2, cnt2, _, _ = _search_vl(me_h, opp_h, 800, 1, 2, use_graph=False, fused=False)
+    assert np.array_equal(cnt2, cnt)
+
+
+@pytest.mark.parametrize("leaves", [2, 3])
+def test_virtual_loss_lockstep_float_priors_vs_c_oracle(leaves):
+    """the same float (w, v) fed to GPU trees and oracle trees every iteration: leaves, statuses, path lengths of every
+    slot and the final statistics must agree bit for bit"""
+    from betazero_b200 import env, mcts
+    from oracle import pyoracle as po
+
+    B, iters = 64, 60
+    me_h, opp_h = po.playout_boards(B, seed=12)
+    pools = mcts.TreePools(B, iters * leaves, c_puct=2.0, n_leaves=leaves)
+    s = mcts.BatchedMCTS(pools, None, use_graph=False)
+    s.reset(env.to_device_u64(me_h), env.to_device_u64(opp_h))
+    trees = [po.OracleTree(po.GAME_REVERSI, 8, 2.0) for _ in range(B)]
+    for t, m, o in zip(trees, me_h, opp_h):
+        t.reset_wire(m, o)
+    rng = np.random.default_rng(1)
+    s.select()
+    for it in range(iters):
+        lm, lo = env.to_host_u64(pools.leaf_me), env.to_host_u64(pools.leaf_opp)
+        st = pools.leaf_status.cpu().numpy()
+        plen = pools.path_len.cpu().numpy()
+        w = (rng.random((leaves * B, 65)) ** 4).astype(np.float32)
+        w[rng.random((leaves * B, 65)) < 0.1] = 0.0
+        v = rng.uniform(-1, 1, leaves * B).astype(np.float32)
+        for i, t in enumerate(trees):
+            for j in range(leaves):
+                r = j * B + i
+                ost, ome, oopp, od = t.select_vl(j)
+                assert (ost, ome, oopp, od) == (int(st[r]), int(lm[r]), int(lo[r]), int(plen[r])), (it, i, j)
+            for j in range(leaves):
+                r = j * B + i
+                t.expand_backup_vl(j, w[r], v[r])
+        s.prior_w.copy_(torch.from_numpy(w))
+        s.value.copy_(torch.from_numpy(v))
+        if it + 1 < iters:
+            s.step()
+        else:
+            s.expand_backup()
+    cnt, pi, q = (x.cpu().numpy() for x in s.root_policy())
+    W, P = _root_W_P(s)
+    for i, t in enumerate(trees):
+        c, w_, p_ = t.root_stats()
+        assert np.array_equal(cnt[i], c) and np.array_equal(W[i], w_) and np.array_equal(P[i], p_)
+    s.check_errors()
