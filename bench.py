@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--net", default="mlp", choices=["mlp", "resnet"])
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--graph-unroll", type=int, default=16)
+    ap.add_argument("--leaves", type=int, default=4,
+                    help="descents per tree and MCTS iteration (virtual loss; 1 = the strictly sequential search). "
+                         "2 and 4 run as lane groups of the tree's warp (wave mode)")
     ap.add_argument("--torch-net", action="store_true",
                     help="evaluate the net with PyTorch/cuBLASLt GEMMs (4 launches) instead of the default: the "
                          "hand-written single-launch tcgen05 MLP kernel + programmatic dependent launch")
@@ -104,7 +107,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- CPU arm
 def cpu_selfplay_sample(n_trees: int, n_sims: int, net_kind: str, hidden: int, budget_s: float, steps: int | None,
-                        warmup: int = 1):
+                        warmup: int = 1, leaves: int = 1):
     """The oracle port on the host cores: C sequential MCTS trees (oracle.c, OpenMP over trees)
     stepped in lockstep with the SAME policy/value net evaluated by PyTorch on the CPU in fp32.
     One step = one n_sims-iteration search from each of n_trees reachable roots."""
@@ -119,12 +122,12 @@ def cpu_selfplay_sample(n_trees: int, n_sims: int, net_kind: str, hidden: int, b
     po.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
     net = netmod.make_net(net_kind, hidden=hidden, seed=0, device="cpu", dtype=torch.float32)
     me, opp = po.playout_boards(n_trees, seed=42)
-    forest = po.OracleForest(n_trees)
+    forest = po.OracleForest(n_trees, leaves=leaves)  # the same search definition as the GPU arm
 
     def one_step():
         forest.reset(me, opp)
         with torch.no_grad():
-            for _ in range(n_sims):
+            for _ in range(n_sims // leaves):
                 forest.select()
                 logits, v = net(torch.from_numpy(forest.planes))
                 w = torch.softmax(logits, dim=-1).numpy()
@@ -143,8 +146,8 @@ def cpu_selfplay_sample(n_trees: int, n_sims: int, net_kind: str, hidden: int, b
     dt = time.perf_counter() - t0
     sims = steps * n_trees * n_sims
     return {"value": sims / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps x {n_trees} trees x {n_sims} sims (C oracle trees, OpenMP {po.num_threads()} threads, "
-                      f"torch fp32 {net_kind} net on CPU, batch {n_trees}); {dt:.1f} s",
+            "sample": f"{steps} steps x {n_trees} trees x {n_sims} sims, {leaves} leaves per iteration (C oracle trees, "
+                      f"OpenMP {po.num_threads()} threads, torch fp32 {net_kind} net on CPU, batch {n_trees * leaves}); {dt:.1f} s",
             "positions_per_sec": steps * n_trees / dt, "ms_per_step": 1e3 * dt / steps, "steps": steps}
 
 
@@ -153,7 +156,7 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     # W warm-up steps, then exactly K timed steps; one step = one search over the bounded sample
-    r2 = cpu_selfplay_sample(args.cpu_trees, args.sims, args.net, args.hidden, 0, args.steps, args.warmup)
+    r2 = cpu_selfplay_sample(args.cpu_trees, args.sims, args.net, args.hidden, 0, args.steps, args.warmup, args.leaves)
     line = {
         "impl": "reference", "metric": METRIC, "value": r2["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r2["steps"], "warmup": args.warmup, "ms_per_step": r2["ms_per_step"], "higher_is_better": True,
@@ -166,17 +169,26 @@ def run_reference(args):
     emit(line)
 
 
-def kernel_net_label(games):
-    if games <= 74 * 128:
+def kernel_net_label(rows):
+    if rows <= 74 * 128:
         return ("bz_mlp_forward_pair (tcgen05 cta_group::2, weights resident in shared memory, one launch) "
                 "+ programmatic dependent launch")
     return "bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch"
 
 
+def search_label(leaves):
+    if leaves <= 1:
+        return "PUCT, one descent per tree and iteration (bit-exact vs oracle/mcts_ref.py MCTS.select)"
+    return (f"PUCT, {leaves} descents per tree and iteration with virtual loss (north_star (b)); bit-exact vs "
+            "oracle/mcts_ref.py MCTS.select_vl")
+
+
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
-            "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "hidden": args.hidden,
-            "net_backend": (kernel_net_label(args.games) if getattr(args, "kernel_net", False) else "PyTorch/cuBLASLt GEMMs"),
+            "games_per_gpu": args.games, "sims_per_move": args.sims, "leaves_per_iteration": args.leaves,
+            "search": search_label(args.leaves), "net": args.net, "hidden": args.hidden,
+            "net_backend": (kernel_net_label(args.games * args.leaves) if getattr(args, "kernel_net", False)
+                            else "PyTorch/cuBLASLt GEMMs"),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -206,17 +218,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    B, S = args.games, args.sims
+    B, S, K = args.games, args.sims, args.leaves
+    if S % K:
+        raise SystemExit("--sims must be a multiple of --leaves")
     net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
     kernel_net = (not args.torch_net) and hasattr(net, "fused_kernel_ok") and net.fused_kernel_ok(
-        torch.empty((1, 2, 8, 8), dtype=torch.bfloat16, device="cuda")) and B <= 148 * 128
+        torch.empty((1, 2, 8, 8), dtype=torch.bfloat16, device="cuda")) and B * K <= 148 * 128
     args.kernel_net = kernel_net
     if hasattr(net, "forward_raw"):
         evaluator = mcts.FusedNetEvaluator(net, use_kernel=None if kernel_net else False)
     else:
         evaluator = mcts.NetEvaluator(net)
     sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
-                                  graph_unroll=args.graph_unroll)
+                                  graph_unroll=args.graph_unroll, n_leaves=K)
     sp.prepare()
     for _ in range(args.warmup):
         sp.play_move()
@@ -270,7 +284,7 @@ def run_b200(args):
     sp.mcts.reset(sp.me, sp.opp)
     sp.mcts.select()
     evs = []
-    n_probe = min(S - 1, 400)
+    n_probe = min(S // K - 1, 400)
     for i in range(n_probe):
         sp.mcts.evaluate()
         # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
@@ -304,10 +318,11 @@ def run_b200(args):
         d = tstats["mean_depth"]
         bmean = tstats["edges"] / max(1, tstats["sims"])  # edges created per iteration ~ mean children of a new node
         bytes_per_sim = 28 * d + 12 * d * bmean + 13 * bmean + 312
-        achieved = bytes_per_sim * B / (step_kernel_ms * 1e-3) / 1e9
+        achieved = bytes_per_sim * B * K / (step_kernel_ms * 1e-3) / 1e9  # B * K simulations per launch
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("mcts_step_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "mcts_step_dram_bytes_per_launch" if K == 1 else f"mcts_step_wave{K}_dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -320,11 +335,13 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "step_kernel<reversi> (K7 expand/backup + K5 select + K6 gather)", "bound": "hbm",
+            "roofline": {"kernel": ("step_kernel<reversi> (K7 expand/backup + K5 select + K6 gather)" if K == 1 else
+                                    f"step_wave_kernel<reversi, {32 // K} lanes per descent> (K7 + K5 + K6, {K} leaves per tree)"),
+                         "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel_ms": step_kernel_ms,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
-                         "sims_per_launch": B},
+                         "sims_per_launch": B * K},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
             "selfplay": sp.stats(),
         }
@@ -334,11 +351,14 @@ def run_b200(args):
             torch.cuda.empty_cache()
             if hasattr(net, "forward_raw"):
                 line["extra"]["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
+                if K != 1:  # the strictly sequential search (one leaf per tree and iteration) on the same workload
+                    line["extra"]["one_leaf_per_iteration"] = alt_backend(torch, mcts, selfplay, net, args, leaves=1,
+                                                                          same_backend=True)
             if args.scale_games and args.scale_games != B:
                 line["extra"]["at_scale"] = at_scale(torch, mcts, selfplay, net, args, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay_sample(
-                args.cpu_trees, S, args.net, args.hidden, args.cpu_seconds, None).items()
+                args.cpu_trees, S, args.net, args.hidden, args.cpu_seconds, None, leaves=K).items()
                 if k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     if world > 1:
@@ -346,15 +366,17 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def alt_backend(torch, mcts, selfplay, net, args):
+def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=False):
     """The headline workload with the OTHER net backend (library GEMMs if the headline used the tcgen05 MLP
-    kernel, and vice versa), so one bench line shows both."""
+    kernel, and vice versa), or with another number of leaves per iteration, so one bench line shows both."""
     from betazero_b200 import _lib as bzlib
 
-    use_kernel = not getattr(args, "kernel_net", False)
+    leaves = args.leaves if leaves is None else leaves
+    use_kernel = getattr(args, "kernel_net", False) if same_backend else not getattr(args, "kernel_net", False)
     try:
         ev = mcts.FusedNetEvaluator(net, use_kernel=None if use_kernel else False)
-        sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll)
+        sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll,
+                                      n_leaves=leaves)
         sp.prepare()
         for _ in range(3):
             sp.play_move()
@@ -368,8 +390,9 @@ def alt_backend(torch, mcts, selfplay, net, args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         sp.mcts.check_errors()
-        return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms,
-                "net_backend": kernel_net_label(args.games) if use_kernel else "PyTorch/cuBLASLt GEMMs"}
+        return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms, "leaves_per_iteration": leaves,
+                "search": search_label(leaves),
+                "net_backend": kernel_net_label(args.games * leaves) if use_kernel else "PyTorch/cuBLASLt GEMMs"}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
     finally:
@@ -399,7 +422,7 @@ def at_scale(torch, mcts, selfplay, net, args, hbm_peak):
         st = sp.mcts.stats()
         d, b = st["mean_depth"], st["edges"] / max(1, st["sims"])
         return {"games_per_gpu": G, "sims_per_sec": G * S / (ms * 1e-3), "positions_per_sec": G / (ms * 1e-3),
-                "ms_per_step": ms, "lanes_per_tree": 8 if G >= 8192 else 32, "mean_depth": d, "mean_children": b,
+                "ms_per_step": ms, "lanes_per_tree": 8 if G >= 32768 else (16 if G >= 8192 else 32), "leaves_per_iteration": 1, "mean_depth": d, "mean_children": b,
                 "pool_bytes": sp.pools.nbytes()}
     except Exception as e:  # never let the side measurement break the headline line
         return {"error": f"{type(e).__name__}: {e}"}
