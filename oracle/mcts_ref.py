@@ -340,16 +340,20 @@ def pick_move(counts) -> int:
     return int(np.argmax(np.asarray(counts)))  # np.argmax returns the first maximum
 
 
-def self_play_game(game, n_sims: int, c_puct: float, evaluator, max_plies: int = 200):
+def self_play_game(game, n_sims: int, c_puct: float, evaluator, max_plies: int = 200, leaves: int = 1):
     """One deterministic self-play game in the order of the reference episode loops
     (reversi_terminal.py:16-38 / tic_tac_toe.py:13-34): search, move (or pass), terminal test,
-    flip player.  Returns a list of (me, opp, player, counts, action) per ply and the winner."""
+    flip player.  Returns a list of (me, opp, player, counts, action) per ply and the winner.
+    ``leaves`` > 1: every search makes that many virtual-loss descents per iteration (MCTS.run_vl)."""
     board, player = game.initial()
     history = []
     while game.terminal_value(board, player) is None and len(history) < max_plies:
         m = MCTS(game, c_puct, evaluator)
         m.reset(board, player)
-        m.run(n_sims)
+        if leaves > 1:
+            m.run_vl(n_sims, leaves)
+        else:
+            m.run(n_sims)
         cnt, _, _ = m.root_stats()
         a = pick_move(cnt)
         me, opp = game.wire(board, player)

@@ -36,18 +36,19 @@ def test_philox_matches_python_restatement():
     assert len(set(exp)) == 6
 
 
-@pytest.mark.parametrize("size,n_sims", [(4, 24), (6, 16)])
-def test_deterministic_selfplay_equals_sequential_oracle(size, n_sims):
+@pytest.mark.parametrize("size,n_sims,leaves", [(4, 24, 1), (6, 16, 1), (4, 24, 4), (6, 16, 2)])
+def test_deterministic_selfplay_equals_sequential_oracle(size, n_sims, leaves):
     """temp_plies = 0 (always the most visited move): every slot plays the same game as the oracle's
-    sequential self_play_game in the order of the reference loop; check records, z and restart."""
+    sequential self_play_game in the order of the reference loop; check records, z and restart.
+    leaves > 1: the searches use virtual loss (wave mode on the GPU, MCTS.run_vl in the oracle)."""
     from betazero_b200 import mcts, selfplay
 
     salt = 3
     game = mr.ReversiGame(po.OracleReversiBoard, size)
-    hist, winner = mr.self_play_game(game, n_sims, 1.25, lambda a, b: mr.hash_eval(a, b, salt, 65))
+    hist, winner = mr.self_play_game(game, n_sims, 1.25, lambda a, b: mr.hash_eval(a, b, salt, 65), leaves=leaves)
     B = 5
     sp = selfplay.BatchedSelfPlay(B, n_sims, mcts.HashEvaluator(salt), board_size=size, temp_plies=0, use_graph=False,
-                                  rank=1, world=3)
+                                  rank=1, world=3, n_leaves=leaves)
     assert sp.game_id.tolist() == [5, 6, 7, 8, 9]  # rank 1 of 3 owns ids rank*B + s
     for ply in range(len(hist)):
         assert sp.ply.tolist() == [ply] * B
