@@ -310,14 +310,74 @@ def mcts_fixtures(RB, TB):
     np.savez_compressed(os.path.join(OUT, "mcts.npz"), **recs)
 
 
+def mcts_vl_fixtures(RB, TB):
+    """Virtual-loss searches (MCTS.run_vl, K descents per iteration) of the definition on the LIVE reference boards:
+    tests/golden/mcts_vl.npz.  Same root sets as mcts.npz's rev8_playout / start position, plus tic-tac-toe games."""
+    recs = {}
+    C_PUCT = 1.25
+
+    def record(prefix, game, roots, n_sims, salt, leaves):
+        A = game.n_actions
+        me, opp, cnt, W, P = [], [], [], [], []
+        for board, player in roots:
+            m = mr.MCTS(game, C_PUCT, lambda a, b: mr.hash_eval(a, b, salt, A))
+            m.reset(board, player)
+            m.run_vl(n_sims, leaves)
+            c, w, p = m.root_stats()
+            a, b = game.wire(board, player)
+            me.append(a)
+            opp.append(b)
+            cnt.append(c)
+            W.append(w)
+            P.append(p)
+        recs[prefix + "_me"] = np.array(me, np.uint64)
+        recs[prefix + "_opp"] = np.array(opp, np.uint64)
+        recs[prefix + "_counts"] = np.stack(cnt)
+        recs[prefix + "_W"] = np.stack(W)
+        recs[prefix + "_P"] = np.stack(P)
+        recs[prefix + "_meta"] = np.array([n_sims, salt, leaves], np.int64)
+        print(prefix, len(roots), "roots", n_sims, "sims", leaves, "leaves")
+
+    rng = np.random.default_rng(7)
+    rg = mr.ReversiGame(RB, 8)
+    roots = []
+    b, cur, over = RB(size=8), 1, False
+    while not over:
+        roots.append((b, cur))
+        moves = b.generate_possible_moves(cur)
+        if moves:
+            r, c = moves[int(rng.integers(len(moves)))]
+            b = b.make_move(r, c, cur)
+        over = b.is_game_over()
+        cur *= -1
+    record("rev8_playout_s48_k2", rg, roots, 48, 3, 2)
+    record("rev8_playout_s48_k4", rg, roots[::2], 48, 3, 4)
+    record("rev8_start_s240_k4", rg, [rg.initial()], 240, 11, 4)
+    tg = mr.TicTacToeGame(TB)
+    for leaves in (2, 4):
+        hist, winner = mr.self_play_game(tg, 48, C_PUCT, lambda a, b: mr.hash_eval(a, b, 1, 9), leaves=leaves)
+        p = f"ttt_game_s48_k{leaves}"
+        recs[p + "_me"] = np.array([h[0] for h in hist], np.uint64)
+        recs[p + "_opp"] = np.array([h[1] for h in hist], np.uint64)
+        recs[p + "_counts"] = np.stack([h[3] for h in hist])
+        recs[p + "_action"] = np.array([h[4] for h in hist], np.uint8)
+        recs[p + "_winner"] = np.array(winner)
+    recs["c_puct"] = np.array(C_PUCT, np.float32)
+    np.savez_compressed(os.path.join(OUT, "mcts_vl.npz"), **recs)
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("reference not found at " + ref_shim.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     RB, TB = ref_shim.reversi_board_cls(), ref_shim.ttt_board_cls()
+    if "--only-vl" in sys.argv:  # the other fixtures are unchanged
+        mcts_vl_fixtures(RB, TB)
+        return
     reversi_env(RB)
     ttt_env(TB)
     mcts_fixtures(RB, TB)
+    mcts_vl_fixtures(RB, TB)
 
 
 if __name__ == "__main__":

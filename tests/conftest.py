@@ -48,3 +48,11 @@ def golden_mcts():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN, "mcts.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_mcts_vl():
+    """virtual-loss searches of the Python definition run on the live reference boards (make_golden.py --only-vl)"""
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN, "mcts_vl.npz"))

@@ -487,3 +487,16 @@ def test_virtual_loss_lockstep_float_priors_vs_c_oracle(leaves):
         c, w_, p_ = t.root_stats()
         assert np.array_equal(cnt[i], c) and np.array_equal(W[i], w_) and np.array_equal(P[i], p_)
     s.check_errors()
+
+
+@pytest.mark.parametrize("group", GROUPS)
+@pytest.mark.parametrize("prefix", ["rev8_playout_s48_k2", "rev8_playout_s48_k4", "rev8_start_s240_k4"])
+def test_virtual_loss_matches_golden(golden_mcts_vl, prefix, group):
+    """golden = the Python definition run on the LIVE reference boards (tests/golden/mcts_vl.npz)"""
+    g = golden_mcts_vl
+    n_sims, salt, leaves = (int(v) for v in g[prefix + "_meta"])
+    s, cnt, pi, q = _search_vl(g[prefix + "_me"], g[prefix + "_opp"], n_sims, salt, leaves, c_puct=float(g["c_puct"]),
+                               group_lanes=group)
+    assert np.array_equal(cnt, g[prefix + "_counts"])
+    W, P = _root_W_P(s)
+    assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])

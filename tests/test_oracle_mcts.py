@@ -152,3 +152,107 @@ def test_reference_headless_loop_accepts_mcts_players(golden_mcts, n_sims):
     p = f"ttt_game_s{n_sims}_k{salt}"
     assert np.array_equal(np.stack(counts), g[p + "_counts"]) and winner == int(g[p + "_winner"])
     assert len(positions) == len(counts) + 1
+
+
+# ---- virtual loss: K descents per iteration (MCTS.select_vl / oracle.c Part 2d) ----------------------------------
+VL_PREFIXES = ["rev8_playout_s48_k2", "rev8_playout_s48_k4", "rev8_start_s240_k4"]
+
+
+@pytest.mark.parametrize("prefix", VL_PREFIXES)
+def test_c_virtual_loss_matches_golden(golden_mcts_vl, prefix):
+    """the C restatement reproduces what the Python definition computed on the LIVE reference boards"""
+    g = golden_mcts_vl
+    n_sims, salt, leaves = (int(v) for v in g[prefix + "_meta"])
+    cnt, W, P, ctr = po.search_hash(g[prefix + "_me"], g[prefix + "_opp"], n_sims, po.GAME_REVERSI, 8,
+                                    float(g["c_puct"]), salt, leaves=leaves)
+    assert np.array_equal(cnt, g[prefix + "_counts"])
+    assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])
+    assert ctr["sims"] == n_sims * len(cnt)
+
+
+@pytest.mark.parametrize("leaves", [2, 4])
+def test_c_virtual_loss_matches_golden_ttt_games(golden_mcts_vl, leaves):
+    g = golden_mcts_vl
+    p = f"ttt_game_s48_k{leaves}"
+    cnt, _, _, _ = po.search_hash(g[p + "_me"], g[p + "_opp"], 48, po.GAME_TTT, 3, float(g["c_puct"]), 1, leaves=leaves)
+    assert np.array_equal(cnt, g[p + "_counts"])
+    assert np.array_equal(np.argmax(cnt, axis=1), g[p + "_action"])
+
+
+def test_python_virtual_loss_definition_on_oracle_boards_matches_golden(golden_mcts_vl):
+    """the definition driven by the C-restated board classes (what the GPU box can run) == driven by the reference"""
+    g = golden_mcts_vl
+    game = mr.ReversiGame(po.OracleReversiBoard, 8)
+    prefix = "rev8_playout_s48_k4"
+    n_sims, salt, leaves = (int(v) for v in g[prefix + "_meta"])
+    for k in range(0, len(g[prefix + "_me"]), 5):
+        board = po.OracleReversiBoard(size=8)
+        board.board = po.wire_to_grid(g[prefix + "_me"][k], g[prefix + "_opp"][k], 8)
+        m = mr.MCTS(game, float(g["c_puct"]), lambda a, b: mr.hash_eval(a, b, salt, 65))
+        m.reset(board, 1)
+        m.run_vl(n_sims, leaves)
+        c, w, p_ = m.root_stats()
+        assert np.array_equal(c, g[prefix + "_counts"][k]) and np.array_equal(w, g[prefix + "_W"][k])
+        assert np.array_equal(p_, g[prefix + "_P"][k])
+
+
+def test_virtual_loss_with_one_leaf_is_the_sequential_search():
+    """K = 1: 'descents that entered the node before' == 1 + sum(child N): same visit counts and priors as MCTS.run;
+    W differs only by the (W - 1) + 1 roundings"""
+    me, opp = po.playout_boards(24, seed=2)
+    c1, W1, P1, k1 = po.search_hash(me, opp, 200, salt=4)
+    trees = [po.OracleTree() for _ in range(len(me))]
+    for t, m, o in zip(trees, me, opp):
+        t.reset_wire(m, o)
+        for _ in range(200):
+            st, lm, lo, _ = t.select_vl(0)
+            w, v = po.hash_eval(lm, lo, 4, 65) if st == 0 else (None, 0.0)
+            t.expand_backup_vl(0, w, v)
+    for i, t in enumerate(trees):
+        c, W, P = t.root_stats()
+        assert np.array_equal(c, c1[i]) and np.array_equal(P, P1[i])
+        np.testing.assert_allclose(W, W1[i], atol=2e-5)
+
+
+def test_virtual_loss_stepwise_c_equals_python_with_float_priors():
+    """random float (w, v) per leaf, 3 leaves per iteration: leaves, statuses, depths and statistics agree"""
+    game = mr.ReversiGame(po.OracleReversiBoard, 8)
+    b, p = game.initial()
+    rng = np.random.default_rng(5)
+    m = mr.MCTS(game, 2.0, None)
+    m.reset(b, p)
+    t = po.OracleTree(po.GAME_REVERSI, 8, 2.0)
+    t.reset(np.asarray(b.board), p)
+    K = 3
+    for it in range(70):
+        evs = []
+        for j in range(K):
+            st, me, opp = m.select_vl(j)
+            cst, cme, copp, cd = t.select_vl(j)
+            assert (st, me, opp) == (cst, cme, copp), (it, j)
+            w = (rng.random(65) ** 3).astype(np.float32)
+            w[rng.random(65) < 0.1] = 0
+            evs.append((w, np.float32(rng.uniform(-1, 1))))
+        for j in range(K):
+            m.expand_backup_vl(j, *evs[j])
+            t.expand_backup_vl(j, *evs[j])
+    for a, b_ in zip(m.root_stats(), t.root_stats()):
+        assert np.array_equal(a, b_)
+    assert t.counters()["sims"] == 70 * K
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="live reference not present")
+def test_virtual_loss_definition_on_live_reference_matches_c():
+    RB = ref_shim.reversi_board_cls()
+    game = mr.ReversiGame(RB, 8)
+    b, p = game.initial()
+    for (r, c) in ((2, 4), (2, 3)):
+        b, p = game.next(b, p, r * 8 + c)
+    m = mr.MCTS(game, 1.25, lambda a, c: mr.hash_eval(a, c, 9, 65))
+    m.reset(b, p)
+    m.run_vl(120, 4)
+    me, opp = game.wire(b, p)
+    cnt, W, P, _ = po.search_hash(np.array([me], np.uint64), np.array([opp], np.uint64), 120, po.GAME_REVERSI, 8, 1.25, 9,
+                                  leaves=4)
+    c0, w0, p0 = m.root_stats()
+    assert np.array_equal(cnt[0], c0) and np.array_equal(W[0], w0) and np.array_equal(P[0], p0)
