@@ -121,9 +121,21 @@ __device__ __forceinline__ void apply_legal(uint64_t &me, uint64_t &opp, unsigne
 // board, where the ">>" senses become "<<", so all lanes run the same left-shift code with a
 // per-lane shift count.  Results are combined with redux.sync OR over the group's lanes.
 // G in {8, 16, 32}; gmask = the group's lanes, gl = lane index inside the group.
+// A whole warp: redux.sync.  Sub-warp groups: a redux with a different member mask per group is serialised group
+// by group (ncu: 12 % of the wave kernel's stall samples), so the groups use an xor butterfly over the full warp
+// instead (lane ^ d stays inside an aligned group of 8 or 16 lanes).  Every lane of the warp must call this together.
 __device__ __forceinline__ uint64_t group_or64(unsigned gmask, uint64_t v) {
-    const unsigned lo = __reduce_or_sync(gmask, (unsigned)v);
-    const unsigned hi = __reduce_or_sync(gmask, (unsigned)(v >> 32));
+    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    if (gmask == 0xFFFFFFFFu) {
+        lo = __reduce_or_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_or_sync(0xFFFFFFFFu, hi);
+    } else {
+        const int g = __popc(gmask);  // 8 or 16
+        for (int d = g >> 1; d; d >>= 1) {
+            lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, d);
+            hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        }
+    }
     return ((uint64_t)hi << 32) | lo;
 }
 
