@@ -6,7 +6,7 @@ from betazero_b200 import env, mcts, net as netmod
 B, S = int(os.environ.get("GAMES", "4096")), int(os.environ.get("SIMS", "800"))
 model = netmod.make_net("mlp", seed=0)
 me, opp, _ = env.reversi_init(B)
-s = mcts.BatchedMCTS(mcts.TreePools(B, S), mcts.FusedNetEvaluator(model), graph_unroll=16)
+s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=int(os.environ.get("LEAVES", "4"))), mcts.FusedNetEvaluator(model), graph_unroll=16)
 s.prepare()
 s.reset(me, opp)
 s.run(S)
