@@ -319,10 +319,18 @@ def run_b200(args):
         bmean = tstats["edges"] / max(1, tstats["sims"])  # edges created per iteration ~ mean children of a new node
         bytes_per_sim = 28 * d + 12 * d * bmean + 13 * bmean + 312
         achieved = bytes_per_sim * B * K / (step_kernel_ms * 1e-3) / 1e9  # B * K simulations per launch
-        traffic = None
+        traffic, issue = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "mcts_step_dram_bytes_per_launch" if K == 1 else f"mcts_step_wave{K}_dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof.get("mcts_step_dram_bytes_per_launch" if K == 1 else f"mcts_step_wave{K}_dram_bytes_per_launch")
+            winst = prof.get("mcts_step_warp_inst_per_launch" if K == 1 else f"mcts_step_wave{K}_warp_inst_per_launch")
+            if winst and B == 4096:
+                # second roofline of the same kernel: warp instructions issued (ncu count per launch at this batch) against
+                # the issue rate of the chip, 148 SMs x 4 schedulers x 1 instruction/clk at the sampled SM clock
+                clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                peak_issue = 148 * 4 * clk
+                issue = {"bound": "issue", "warp_inst_per_launch": winst, "achieved": winst / (step_kernel_ms * 1e-3) / 1e9,
+                         "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": winst / (step_kernel_ms * 1e-3) / peak_issue}
         except Exception:
             pass
         line = {
@@ -341,7 +349,7 @@ def run_b200(args):
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel_ms": step_kernel_ms,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
-                         "sims_per_launch": B * K},
+                         "sims_per_launch": B * K, "issue": issue},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
             "selfplay": sp.stats(),
         }

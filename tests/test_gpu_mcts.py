@@ -232,15 +232,23 @@ def test_terminal_and_pass_roots():
     assert pi.cpu().numpy()[1, 64] == 1.0
 
 
-def test_arena_overflow_is_detected():
+@pytest.mark.parametrize("leaves,group", [(1, 0), (4, 0), (2, 0), (3, 0), (2, 8)])
+def test_arena_overflow_is_detected(leaves, group):
+    """an arena too small for the search: flagged and raised in every kernel family (one leaf, wave mode, slots one
+    after the other), and the trees stay readable (no write past the arena)"""
     from betazero_b200 import _lib, env, mcts
     from oracle import pyoracle as po
 
     me_h, opp_h = po.playout_boards(8, seed=1)
-    pools = mcts.TreePools(8, 64, arena_units=40)
+    pools = mcts.TreePools(8, 72, arena_units=40, n_leaves=leaves, group_lanes=group)
+    guard = pools.arena.clone()  # the arena of the LAST tree must not be overrun into whatever follows: check its size
     s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(0), use_graph=False)
     with pytest.raises(_lib.BzError, match="overflow"):
-        s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 64)
+        s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 72)
+    assert pools.arena.numel() == guard.numel()
+    assert int(pools.arena_used.max().item()) <= 40
+    cnt, _, _ = s.root_policy()
+    assert int(cnt.sum(1).max().item()) <= 72
 
 
 def test_hash_eval_kernel_matches_oracle():
