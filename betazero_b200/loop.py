@@ -31,7 +31,8 @@ def run(args) -> list[dict]:
     opt = torch.optim.Adam(master.parameters(), lr=args.lr)  # the reference's optimiser family (SL/train.py:87)
     evaluator = mcts.FusedNetEvaluator(model) if hasattr(model, "forward_raw") else mcts.NetEvaluator(model)
     sp = selfplay.BatchedSelfPlay(args.games, args.sims, evaluator, board_size=args.size, temp_plies=args.temp_plies,
-                                  seed=args.seed, rank=rank, world=world, graph_unroll=min(16, max(1, args.sims - 1)))
+                                  seed=args.seed, rank=rank, world=world, n_leaves=args.leaves,
+                                  graph_unroll=min(16, max(1, args.sims // args.leaves - 1)))
     sp.prepare()
     out = []
     for it in range(args.iterations):
@@ -83,6 +84,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--leaves", type=int, default=4, help="virtual-loss descents per tree and iteration (1 = sequential search)")
     ap.add_argument("--plies", type=int, default=70, help="lockstep plies per iteration (a game lasts ~60)")
     ap.add_argument("--size", type=int, default=8)
     ap.add_argument("--iterations", type=int, default=1)
