@@ -508,3 +508,17 @@ def test_virtual_loss_matches_golden(golden_mcts_vl, prefix, group):
     assert np.array_equal(cnt, g[prefix + "_counts"])
     W, P = _root_W_P(s)
     assert np.array_equal(W, g[prefix + "_W"]) and np.array_equal(P, g[prefix + "_P"])
+
+
+@pytest.mark.parametrize("leaves", [1, 4])
+def test_path_depth_overflow_is_detected(leaves):
+    """max_depth smaller than the trees grow: code 2 is flagged and raised, nothing is written past the path records"""
+    from betazero_b200 import _lib, env, mcts
+    from oracle import pyoracle as po
+
+    me_h, opp_h = po.playout_boards(16, seed=4)
+    pools = mcts.TreePools(16, 200, max_depth=2, n_leaves=leaves)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(0), use_graph=False)
+    with pytest.raises(_lib.BzError, match="path depth"):
+        s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 200)
+    assert int(pools.path_len.max().item()) <= 2
