@@ -155,6 +155,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
+    # the same config object as the GPU arm prints for these arguments (the CPU arm itself evaluates the net with torch on
+    # the host cores; `net_backend` names what the GPU arm uses)
+    args.kernel_net = (not args.torch_net) and args.net == "mlp" and args.hidden == 256 and args.games * args.leaves <= 148 * 128
     # W warm-up steps, then exactly K timed steps; one step = one search over the bounded sample
     r2 = cpu_selfplay_sample(args.cpu_trees, args.sims, args.net, args.hidden, 0, args.steps, args.warmup, args.leaves)
     line = {
