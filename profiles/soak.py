@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import torch
 from betazero_b200 import mcts, net, selfplay
 model = net.make_net("mlp", seed=0)
-sp = selfplay.BatchedSelfPlay(4096, 800, mcts.FusedNetEvaluator(model), temp_plies=8, seed=7, dirichlet_alpha=0.3)
+sp = selfplay.BatchedSelfPlay(4096, 800, mcts.FusedNetEvaluator(model), temp_plies=8, seed=7, dirichlet_alpha=0.3, n_leaves=int(sys.argv[1]) if len(sys.argv) > 1 else 4)
 sp.prepare()
 t = time.time()
 for i in range(200):
