@@ -81,6 +81,7 @@ SIGNATURES = {
     "bz_mlp_forward_image": [ptr] * 7 + [_I64, ptr],
     "bz_mlp_forward_pair": [ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_pair_image_bytes": [],
+    "bz_mlp_forward_pair2": [ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_forward_packed": [ptr, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_weight_image_bytes": [],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],

@@ -88,4 +88,86 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&v);
 }
 
+// ---- CTA pairs (clusters of 2, tcgen05 cta_group::2): used by mlp_pair.cu and mlp_pair2.cu -------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// relaxed: the only cross-CTA state published through these barriers is the mbarrier initialisation (which has its own
+// fence.mbarrier_init.release.cluster) and "my tcgen05.ld have completed" (tcgen05 fences); a releasing arrive costs ~1000 clk
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics (release at
+// CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses for its 2-SM pipelines: the data the leader's MMA
+// will read sits in THIS CTA's shared memory and was made visible to the async proxy by its writers' fence.proxy.async
+// before the CTA-local barrier.  A .release.cluster arrive was measured at 0.25 - 0.9 us per handshake (longest while
+// bulk copies are in flight on the SM); this form at 0.06 - 0.12 us.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// (a0 + b0, a1 + b1), each sum rounded to fp32 (FADD2: one issue slot for two adds)
+__device__ __forceinline__ float2 add2(uint32_t a0, uint32_t a1, float b0, float b1) {
+    uint64_t a, b, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    float2 f;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(r));
+    return f;
+}
+// bf16x2 {lo = relu(v.x), hi = relu(v.y)}, round to nearest even: max(x, 0) and the rounding commute
+__device__ __forceinline__ uint32_t pack_relu_bf16(float2 v) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+    return d;
+}
+
+__device__ __forceinline__ uint4 bias_pack8(const uint32_t *acc, const float *bias) {
+    const float4 b0 = *reinterpret_cast<const float4 *>(bias), b1 = *reinterpret_cast<const float4 *>(bias + 4);
+    const float2 s0 = add2(acc[0], acc[1], b0.x, b0.y), s1 = add2(acc[2], acc[3], b0.z, b0.w);
+    const float2 s2 = add2(acc[4], acc[5], b1.x, b1.y), s3 = add2(acc[6], acc[7], b1.z, b1.w);
+    uint4 v;
+    v.x = pack_bf16(s0.x, s0.y);
+    v.y = pack_bf16(s1.x, s1.y);
+    v.z = pack_bf16(s2.x, s2.y);
+    v.w = pack_bf16(s3.x, s3.y);
+    return v;
+}
+
 }  // namespace bz

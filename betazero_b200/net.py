@@ -142,6 +142,8 @@ class PolicyValueMLP(nn.Module):
             fused = self.fused_kernel_ok(planes) and B <= 148 * 128
             if fused and B <= 74 * 128:
                 fused = "pair"
+            elif fused and getattr(self, "_image_pair", None) is not None:
+                fused = "pair2"  # 74 pairs x 256 rows = 18 944 rows in one wave
         if fused:
             from . import _lib
 
@@ -156,6 +158,10 @@ class PolicyValueMLP(nn.Module):
             hw, hb = self._head_full
             x = planes.reshape(B, -1)
             L = _lib.load()
+            if fused == "pair2" and getattr(self, "_image_pair", None) is not None:  # CTA pairs, two tiles per pair
+                _lib.check(L.bz_mlp_forward_pair2(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B,
+                                                  _lib.stream_ptr()), "bz_mlp_forward_pair2")
+                return out
             if fused == "pair" and getattr(self, "_image_pair", None) is not None:  # CTA pairs, weights resident
                 _lib.check(L.bz_mlp_forward_pair(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B,
                                                  _lib.stream_ptr()), "bz_mlp_forward_pair")

@@ -338,6 +338,12 @@ int bz_mlp_forward_image(const void *x_bf16, const void *weight_image32, const v
 int bz_mlp_forward_pair(const void *x_bf16, const void *weight_image_pair, void *out_bf16, int64_t n,
                         bz_stream_t stream);
 int64_t bz_mlp_pair_image_bytes(void);
+/* The pair kernel for 9 473 .. 18 944 rows: every pair owns TWO 128-row tiles and ping-pongs them (a control warp
+ * issues the MMAs of one tile while the 16 epilogue warps convert the other), so 16 384 rows are one wave of 128 CTAs
+ * and the tensor cores do not idle during the epilogues; the two 64 KB weight regions of a CTA are recycled layer by
+ * layer.  Same weight image, x / out and results as bz_mlp_forward_pair. */
+int bz_mlp_forward_pair2(const void *x_bf16, const void *weight_image_pair, void *out_bf16, int64_t n,
+                         bz_stream_t stream);
 
 /* The same network as a warp-specialised, software-pipelined kernel (MMA issuer / weight producer /
  * 16 epilogue warps; TMEM and activation double buffering, cp.async.bulk weight streaming).

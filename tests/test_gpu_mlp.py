@@ -19,8 +19,8 @@ def _planes(B, seed):
 
 # True: bz_mlp_forward_image (TMA weights); "ldgsts": bz_mlp_forward (raw weights); "v2": pipelined bz_mlp_forward_packed;
 # "pair": bz_mlp_forward_pair (cta_group::2, weights resident)
-@pytest.mark.parametrize("variant", [True, "ldgsts", "v2", "pair"])
-@pytest.mark.parametrize("B", [1, 7, 64, 65, 128, 129, 1000, 4096])
+@pytest.mark.parametrize("variant", [True, "ldgsts", "v2", "pair", "pair2"])
+@pytest.mark.parametrize("B", [1, 7, 64, 65, 128, 129, 257, 1000, 4096])
 def test_fused_mlp_matches_torch_module(B, variant):
     from betazero_b200 import net
 
@@ -60,7 +60,7 @@ def test_fused_mlp_is_deterministic_and_row_independent():
     assert torch.equal(a, b)
     c = m.forward_raw(x[37:38].contiguous(), fused=True)
     assert torch.equal(c[0], a[37])  # a row's result does not depend on its batch
-    for other in ("v2", "ldgsts", "pair"):
+    for other in ("v2", "ldgsts", "pair", "pair2"):
         assert torch.equal(a, m.forward_raw(x, fused=other))  # same accumulation order (K ascending, fp32 in TMEM)
 
 
