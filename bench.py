@@ -157,7 +157,7 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     # the same config object as the GPU arm prints for these arguments (the CPU arm itself evaluates the net with torch on
     # the host cores; `net_backend` names what the GPU arm uses)
-    args.kernel_net = (not args.torch_net) and args.net == "mlp" and args.hidden == 256 and args.games * args.leaves <= 148 * 128
+    args.kernel_net = (not args.torch_net) and args.net == "mlp" and args.hidden == 256
     # W warm-up steps, then exactly K timed steps; one step = one search over the bounded sample
     r2 = cpu_selfplay_sample(args.cpu_trees, args.sims, args.net, args.hidden, 0, args.steps, args.warmup, args.leaves)
     line = {
@@ -176,7 +176,8 @@ def kernel_net_label(rows):
     if rows <= 74 * 128:
         return ("bz_mlp_forward_pair (tcgen05 cta_group::2, weights resident in shared memory, one launch) "
                 "+ programmatic dependent launch")
-    return "bz_mlp_forward_image (tcgen05 + TMA weights, one launch) + programmatic dependent launch"
+    return ("bz_mlp_forward_pair2 (tcgen05 cta_group::2, two ping-ponged 128-row tiles per CTA pair, one launch) "
+            "+ programmatic dependent launch")
 
 
 def search_label(leaves):
@@ -226,7 +227,7 @@ def run_b200(args):
         raise SystemExit("--sims must be a multiple of --leaves")
     net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
     kernel_net = (not args.torch_net) and hasattr(net, "fused_kernel_ok") and net.fused_kernel_ok(
-        torch.empty((1, 2, 8, 8), dtype=torch.bfloat16, device="cuda")) and B * K <= 148 * 128
+        torch.empty((1, 2, 8, 8), dtype=torch.bfloat16, device="cuda"))
     args.kernel_net = kernel_net
     if hasattr(net, "forward_raw"):
         evaluator = mcts.FusedNetEvaluator(net, use_kernel=None if kernel_net else False)

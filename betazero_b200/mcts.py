@@ -198,7 +198,7 @@ class FusedNetEvaluator:
         # 1 when the forward is one kernel of libbetazero_b200 (bench.py's gpu_launches), 0 for library GEMMs
         k = self.use_kernel
         if k is None:
-            k = hasattr(self.net, "fused_kernel_ok") and self.net.fused_kernel_ok(pools.leaf_planes) and B <= 148 * 128
+            k = hasattr(self.net, "fused_kernel_ok") and self.net.fused_kernel_ok(pools.leaf_planes)
         self.own_launches = 1 if k else 0
         return self.out, self.value
 

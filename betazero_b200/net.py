@@ -130,20 +130,21 @@ class PolicyValueMLP(nn.Module):
         ``fused=True``: the one-CTA-per-128-rows kernel with TMA weight streaming (``bz_mlp_forward_image``),
         ``"ldgsts"`` the same kernel on the raw nn.Linear weights (``bz_mlp_forward``);
         ``fused="v2"``: its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).
+        ``fused="pair2"``: the pair kernel with two ping-ponged tiles per pair (``bz_mlp_forward_pair2``).
         ``fused=None`` (default) picks, for the supported shape, the pair kernel while one wave of CTA pairs
-        covers the batch (<= 74 x 128 rows), the one-CTA kernel up to 148 x 128 rows, else the library GEMMs.
-        All kernels give bit-identical outputs.  Measured on B200 at 4096 rows, per MCTS iteration with
-        programmatic dependent launch: library 22.3 us, one-CTA kernel 19.0 us, pair kernel 15.9 us
-        (profiles/README.md)."""
+        covers the batch (<= 74 x 128 rows) and the two-tile pair kernel above that; other shapes use the
+        library GEMMs.  All kernels give bit-identical outputs.  Measured on B200 per forward (graph, back
+        to back): 4096 rows pair 6.8 us / one-CTA 12.1 / cuBLASLt 11.8; 16 384 rows pair2 9.9 / 12.7 / 19.8;
+        65 536 rows pair2 34.5 / 45.5 / 52.4 (profiles/README.md)."""
         if self._head is None:
             self.prepare_inference()
         B = planes.shape[0]
-        if fused is None:  # auto: a single-launch kernel while one wave of CTAs covers the batch
-            fused = self.fused_kernel_ok(planes) and B <= 148 * 128
-            if fused and B <= 74 * 128:
-                fused = "pair"
-            elif fused and getattr(self, "_image_pair", None) is not None:
-                fused = "pair2"  # 74 pairs x 256 rows = 18 944 rows in one wave
+        if fused is None:  # auto: the hand-written kernels for the supported shape, at every batch size
+            fused = self.fused_kernel_ok(planes)
+            if fused and getattr(self, "_image_pair", None) is not None:
+                # one wave of CTA pairs with one 128-row tile each (lowest latency) up to 74 pairs; above that every
+                # pair ping-pongs two tiles (measured faster than cuBLASLt up to at least 131 072 rows)
+                fused = "pair" if B <= 74 * 128 else "pair2"
         if fused:
             from . import _lib
 

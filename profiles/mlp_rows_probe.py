@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from betazero_b200 import net as netmod
 m = netmod.make_net("mlp", seed=0)
-for rows in (4096, 8192, 16384, 32768):
+for rows in (4096, 8192, 16384, 32768, 65536, 131072):
     x = (torch.rand((rows, 2, 8, 8), device="cuda") > 0.6).to(torch.bfloat16)
     out = torch.empty((rows, 72), dtype=torch.bfloat16, device="cuda")
     res = []
