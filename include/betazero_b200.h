@@ -179,7 +179,9 @@ typedef struct bz_tree_pools {
                             K descents per tree and iteration with VIRTUAL LOSS (a descent leaves N += 1, W -= 1 on its
                             edges until its backup): the pending-leaf arrays below then hold K * n_trees entries, slot-major
                             (entry slot * n_trees + tree), eval_out / value have K * n_trees rows, and an iteration counts
-                            K simulations.  Definition and oracle: oracle/mcts_ref.py MCTS.select_vl / expand_backup_vl. */
+                            K simulations.  K = 2 / 4 with group_lanes 0 or 32 run in "wave mode" (the K descents are the
+                            32/K-lane groups of the tree's warp, one level apart); other combinations handle the slots one
+                            after the other.  Definition and oracle: oracle/mcts_ref.py MCTS.select_vl / expand_backup_vl. */
     /* per tree [n_trees] */
     uint64_t *root_me, *root_opp;
     uint32_t *root_meta;  /* like an edge's meta, for the (virtual) edge into the root */

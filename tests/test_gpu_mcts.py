@@ -522,3 +522,16 @@ def test_path_depth_overflow_is_detected(leaves):
     with pytest.raises(_lib.BzError, match="path depth"):
         s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), 200)
     assert int(pools.path_len.max().item()) <= 2
+
+
+def test_virtual_loss_large_batch_stays_in_wave_mode():
+    """>= 8192 trees with 4 leaves per iteration: still the wave kernels (a warp per tree); same answers"""
+    from oracle import pyoracle as po
+
+    B, S = 8192 + 3, 64
+    me_h, opp_h = po.playout_boards(256, seed=9)
+    me_h, opp_h = np.resize(me_h, B), np.resize(opp_h, B)
+    s, cnt, _, _ = _search_vl(me_h, opp_h, S, 2, 4)
+    r_cnt, _, _, _ = po.search_hash(me_h[:256], opp_h[:256], S, po.GAME_REVERSI, 8, 1.25, 2, leaves=4)
+    assert np.array_equal(cnt[:256], r_cnt)
+    assert np.array_equal(cnt[256:512], r_cnt) and np.array_equal(cnt[-3:], r_cnt[(B - 3) % 256:][:3])
