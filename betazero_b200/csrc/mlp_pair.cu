@@ -2,11 +2,11 @@
 //
 // Why a second kernel: at the self-play batch (4096 leaves) the net is a latency chain, not a throughput problem.
 // With one CTA per 128 leaves (mlp.cu) a hidden layer costs 16 MMAs x 128 clk (M = 128, N = 256 on one SM) plus
-// 128 KB of accumulator read-out at the 64 B/clk TMEM read rate, and the next layer's 128 KB of weights can only be
-// fetched once the previous ones have been consumed (they do not fit beside the activations).  Two CTAs of a
-// cluster sharing one 128-leaf tile halve all three terms:
+// the epilogue of 128 x 256 accumulators (bias, ReLU, bf16, swizzled st.shared: ~1 us), and the next layer's 128 KB of
+// weights can only be fetched once the previous ones have been consumed (they do not fit beside the activations).
+// Two CTAs of a cluster sharing one 128-leaf tile halve all three terms:
 //   * the pair executes ONE M = 128, N = 256 MMA per K step (64 leaves per SM): 64 clk instead of 128;
-//   * each SM reads out only its own 64 x 256 accumulators (64 KB);
+//   * each SM converts only its own 64 x 256 accumulators;
 //   * each SM holds HALF of every weight matrix (the B operand of a cta_group::2 MMA is split across the pair by
 //     N), 180 KB for all four layers, so the whole net is fetched once, at kernel start, by four bulk copies
 //     that do not wait for the tree kernel (programmatic dependent launch) -- no weight wait between layers.

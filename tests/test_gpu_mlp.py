@@ -137,3 +137,30 @@ def test_pdl_flag_does_not_leak_into_searches_without_a_kernel_between_steps():
         assert _lib._pdl_state is False
     assert torch.equal(res[0], res[1])
     _lib.set_pdl(False)
+
+
+def test_pair_kernels_are_race_free_under_repetition():
+    """The pair kernels synchronise two CTAs per tile with mbarriers in each other's shared memory: hammer them (with and
+    without the launch attribute for programmatic dependent launch, back to back on one stream) and require bit-identical
+    results every time -- a missed ordering between the epilogue stores and the peer-issued MMAs would show up here."""
+    from betazero_b200 import _lib, net
+
+    m = net.make_net("mlp", seed=11)
+    m.prepare_inference()
+    try:
+        for B, mode in ((4096, "pair"), (16384, "pair2"), (777, "pair"), (9999, "pair2")):
+            x = _planes(B, B + 1)
+            ref = m.forward_raw(x, fused=True).clone()
+            out = torch.empty_like(ref)
+            for pdl in (False, True):
+                _lib.set_pdl(pdl)
+                bad = 0
+                for it in range(200):
+                    out.fill_(0)
+                    m.forward_raw(x, out=out, fused=mode)
+                    if it % 20 == 19:
+                        bad += int(not torch.equal(out, ref))
+                torch.cuda.synchronize()
+                assert bad == 0 and torch.equal(out, ref), (B, mode, pdl)
+    finally:
+        _lib.set_pdl(False)
