@@ -96,6 +96,9 @@ def lib_path() -> str:
     return _build.LIB
 
 
+ABI_VERSION = 2  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
+
+
 def load():
     """dlopen the CUDA library, building it first if needed.  Fails loudly."""
     global _lib
@@ -114,6 +117,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "bz_error_string" else (C.c_int64 if name.endswith("_bytes") else C.c_int)
+    if lib.bz_abi_version() != ABI_VERSION:  # a stale prebuilt library: the struct layouts would not match
+        raise BzError(f"libbetazero_b200.so has ABI version {lib.bz_abi_version()}, this package needs {ABI_VERSION}; rebuild it")
     _lib = lib
     return lib
 

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert lib.bz_abi_version() == 2
+    assert lib.bz_abi_version() == _lib.ABI_VERSION == 2
     assert lib.bz_error_string(0) == b"ok" and b"argument" in lib.bz_error_string(-1)
 
 
@@ -81,3 +81,16 @@ def test_product_never_imports_the_oracle():
             assert "liboracle" not in txt and "pyoracle" not in txt, f"{f} references the oracle library"
             assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
             assert not re.search(r"#include\s+[\"<].*oracle", txt), f"{f} includes oracle code"
+
+
+def test_abi_version_has_one_source_of_truth():
+    """the header, the ctypes mirror and the driver's build() check must agree (build() once asserted a literal)"""
+    import re
+
+    from betazero_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "betazero_b200.h")).read()
+    assert int(re.search(r"#define BZ_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION
+    entry = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert "bz_abi_version() == _lib.ABI_VERSION" in entry
