@@ -254,7 +254,6 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = sp.total_launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
     sp.mcts.check_errors()
     tstats = sp.mcts.stats()  # d and b of the last search
 
@@ -281,6 +280,7 @@ def run_b200(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (value and e2e)
     h2d = 2 * B * 8
     d2h = B * 65 * 4 + B
 
