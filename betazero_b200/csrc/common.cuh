@@ -52,6 +52,22 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is per device: a process that
+// drives several GPUs must set it on each)
+template <typename K>
+inline cudaError_t allow_dynamic_smem(K kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!done[dev]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // streaming (read-once / write-once) 128-bit global accesses that do not allocate in L1

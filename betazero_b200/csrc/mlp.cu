@@ -425,11 +425,10 @@ extern "C" int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1
     if (!aligned16(x_bf16) || !aligned16(w1) || !aligned16(w2) || !aligned16(w3) || !aligned16(w_head) || !aligned16(out_bf16))
         return BZ_ERR_UNALIGNED;
     if (n == 0) return BZ_OK;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    static bool configured[64] = {};
+    {
+        cudaError_t e = allow_dynamic_smem(mlp_kernel, kSmemTotal, configured);
         if (e != cudaSuccess) return cuda_rc(e);
-        configured = true;
     }
     MlpParams p;
     p.x = (const __nv_bfloat16 *)x_bf16;
@@ -451,11 +450,10 @@ extern "C" int bz_mlp_forward_packed(const void *x_bf16, const void *weight_imag
     if (n < 0 || (n && (!x_bf16 || !weight_image || !bias_f32 || !out_bf16))) return BZ_ERR_ARG;
     if (!aligned16(x_bf16) || !aligned16(weight_image) || !aligned16(bias_f32) || !aligned16(out_bf16)) return BZ_ERR_UNALIGNED;
     if (n == 0) return BZ_OK;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    static bool configured[64] = {};
+    {
+        cudaError_t e = allow_dynamic_smem(mlp_pipe_kernel, kSmem2, configured);
         if (e != cudaSuccess) return cuda_rc(e);
-        configured = true;
     }
     Mlp2Params p;
     p.x = (const __nv_bfloat16 *)x_bf16;
@@ -484,11 +482,10 @@ extern "C" int bz_mlp_forward_image(const void *x_bf16, const void *weight_image
     if (n < 0 || (n && (!x_bf16 || !weight_image32 || !b1 || !b2 || !b3 || !b_head || !out_bf16))) return BZ_ERR_ARG;
     if (!aligned16(x_bf16) || !aligned16(weight_image32) || !aligned16(out_bf16)) return BZ_ERR_UNALIGNED;
     if (n == 0) return BZ_OK;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    static bool configured[64] = {};
+    {
+        cudaError_t e = allow_dynamic_smem(mlp_kernel, kSmemTotal, configured);
         if (e != cudaSuccess) return cuda_rc(e);
-        configured = true;
     }
     MlpParams p = {};
     p.x = (const __nv_bfloat16 *)x_bf16;

@@ -267,11 +267,10 @@ extern "C" int bz_mlp_forward_pair(const void *x_bf16, const void *weight_image_
     if (n < 0 || (n && (!x_bf16 || !weight_image_pair || !out_bf16))) return BZ_ERR_ARG;
     if (!aligned16(x_bf16) || !aligned16(weight_image_pair) || !aligned16(out_bf16)) return BZ_ERR_UNALIGNED;
     if (n == 0) return BZ_OK;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    static bool configured[64] = {};
+    {
+        cudaError_t e = allow_dynamic_smem(mlp_pair_kernel, kSmemTotal, configured);
         if (e != cudaSuccess) return cuda_rc(e);
-        configured = true;
     }
     PairParams p = {};
     p.x = (const __nv_bfloat16 *)x_bf16;
