@@ -285,23 +285,60 @@ def run_b200(args):
     d2h = B * 65 * 4 + B
 
     # ---- the dominant kernel (fused expand/backup + select + gather), timed launch by launch ------
-    sp.mcts.reset(sp.me, sp.opp)
-    sp.mcts.select()
-    evs = []
-    n_probe = min(S // K - 1, 400)
-    for i in range(n_probe):
-        sp.mcts.evaluate()
-        # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
-        # (eager launches are CPU-bound; without this the interval would include a launch gap)
-        torch.cuda._sleep(60_000)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        sp.mcts.step()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    k_ms = [a.elapsed_time(b) for a, b in evs]
-    step_kernel_ms = sum(k_ms[len(k_ms) // 2:]) / max(1, len(k_ms) - len(k_ms) // 2)  # deep-tree half
+    # Preferred: CUDA events recorded INSIDE a replayed graph (event-record nodes, torch `external=True`): 16 iterations of
+    # [net, event, tree kernel, event] replayed on the deep-tree half of a search -- the interval holds the kernel and the
+    # ~1 us dependency latency of a graph edge, not an eager launch.  Fallback: eager launches behind a busy GPU.
+    n_iter = S // K - 1
+    step_kernel_ms, probe_kind = None, None
+    try:
+        pairs = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                 for _ in range(16)]
+        sp.mcts.reset(sp.me, sp.opp)
+        sp.mcts.select()
+        for _ in range(2):  # warm-up of the exact sequence that is captured
+            sp.mcts.evaluate()
+            sp.mcts.step()
+        pg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pg):
+            for a, b in pairs:
+                sp.mcts.evaluate()
+                a.record()
+                sp.mcts.step()
+                b.record()
+        sp.mcts.reset(sp.me, sp.opp)
+        sp.mcts.select()
+        k_ms = []
+        done = 0
+        while done + 16 <= n_iter:
+            pg.replay()
+            done += 16
+            if done * 2 >= n_iter:  # deep-tree half
+                torch.cuda.synchronize()
+                k_ms += [a.elapsed_time(b) for a, b in pairs]
+        torch.cuda.synchronize()
+        if k_ms:
+            step_kernel_ms, probe_kind = sum(k_ms) / len(k_ms), "events inside a replayed CUDA graph"
+    except Exception as e:  # older torch without external events, or capture refused: fall back
+        print(f"graph-event probe unavailable ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
+    if step_kernel_ms is None:
+        sp.mcts.reset(sp.me, sp.opp)
+        sp.mcts.select()
+        evs = []
+        n_probe = min(n_iter, 400)
+        for i in range(n_probe):
+            sp.mcts.evaluate()
+            # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
+            # (eager launches are CPU-bound; without this the interval would include a launch gap)
+            torch.cuda._sleep(60_000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sp.mcts.step()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        k_ms = [a.elapsed_time(b) for a, b in evs]
+        step_kernel_ms = sum(k_ms[len(k_ms) // 2:]) / max(1, len(k_ms) - len(k_ms) // 2)  # deep-tree half
+        probe_kind = "eager launches behind a busy GPU (includes ~4 us of launch latency)"
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -352,6 +389,7 @@ def run_b200(args):
                          "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel_ms": step_kernel_ms,
+                         "kernel_ms_probe": probe_kind,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
                          "sims_per_launch": B * K, "issue": issue},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
