@@ -102,3 +102,25 @@ def test_arena_result_equals_reference_terminal_loop(capsys, monkeypatch):
     game.play()
     capsys.readouterr()
     assert game.board.get_score() == (w, counts)
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference (the CPU arm) on a tiny sample: exactly one stdout line, the contract's keys"""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-trees", "8", "--sims", "16",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["config"]["leaves_per_iteration"] == 4
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
