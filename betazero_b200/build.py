@@ -6,6 +6,8 @@ The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -33,23 +35,61 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+STAMP = LIB + ".srchash"  # hash of the sources the library was built from (travels with the .so, like it git-ignored)
+
+
+def _deps():
+    return sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "betazero_b200.h")])
+
+
+def source_hash() -> str:
+    """Content hash of every source the library depends on (+ the compiler flags).  Staleness is decided by CONTENT,
+    not by mtimes: a snapshot copied to another box does not keep file times, and a rebuild started by every rank of a
+    torchrun job at once is exactly the race this avoids."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + list(SOURCES)).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "betazero_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    try:
+        return open(STAMP).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build under an inter-process lock, into a temporary file that is renamed over the library: concurrent ranks
+    either find a complete, current library or wait for the one rank that is building it."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *sources()]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd))
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+            with open(STAMP + ".tmp", "w") as f:
+                f.write(source_hash())
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -25,11 +25,42 @@ _SO = os.path.join(_HERE, "liboracle.so")
 _lib = None
 
 
+def _src_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("oracle.c", "Makefile"):
+        with open(os.path.join(_HERE, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """Compile oracle.c -> liboracle.so (gcc, see Makefile)."""
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    """Compile oracle.c -> liboracle.so (gcc, see Makefile).  Staleness is decided by a content hash kept beside the
+    library (file times do not survive a copy to another box) and the build runs under an inter-process lock, so the
+    ranks of a torchrun job never compile -- or load a half-written library -- at the same time."""
+    import fcntl
+
+    stamp = _SO + ".srchash"
+
+    def stale():
+        try:
+            return not os.path.exists(_SO) or open(stamp).read().strip() != _src_hash()
+        except OSError:
+            return True
+
+    if not force and not stale():
+        return _SO
+    with open(_SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():
+                subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+                with open(stamp + ".tmp", "w") as f:
+                    f.write(_src_hash())
+                os.replace(stamp + ".tmp", stamp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

@@ -94,3 +94,37 @@ def test_abi_version_has_one_source_of_truth():
     assert int(re.search(r"#define BZ_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION
     entry = open(os.path.join(root, "__graft_entry__.py")).read()
     assert "bz_abi_version() == _lib.ABI_VERSION" in entry
+
+
+def test_library_staleness_is_decided_by_content_not_by_file_times():
+    """a snapshot copied to the GPU box does not keep mtimes; a rebuild there, started by every rank of a torchrun job
+    at once, once produced 'file too short' on dlopen"""
+    from betazero_b200 import build as bz_build
+
+    bz_build.build()
+    assert not bz_build.needs_build()
+    src = os.path.join(bz_build.CSRC, "env.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src, None)  # newer than the library
+        assert not bz_build.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+
+
+def test_concurrent_oracle_builds_do_not_race():
+    """four processes find the oracle library stale at the same time: one builds under the lock, all of them load a
+    complete library"""
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stamp = os.path.join(root, "oracle", "liboracle.so.srchash")
+    if os.path.exists(stamp):
+        os.remove(stamp)
+    code = ("import sys; sys.path.insert(0, %r); from oracle import pyoracle as po; "
+            "import numpy as np; m = po.legal_mask(np.array([0x0000000810000000], np.uint64), np.array([0x0000001008000000], np.uint64)); "
+            "print(int(m[0]))" % root)
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in range(4)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-500:] for o in outs]
+    assert len({o[0].strip() for o in outs}) == 1 and os.path.exists(stamp)
