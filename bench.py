@@ -56,7 +56,9 @@ def parse():
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 50 ms DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms DURING the timed regions.  nvidia-smi takes 50-200 ms
+    to deliver its first line, so it is started before the warm-up and every line is stamped on arrival; stop() keeps
+    the lines that arrived inside the windows marked by window_begin() / window_end() (the timed regions)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -64,6 +66,15 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.windows, self._t0 = [], None
+
+    def window_begin(self):
+        self._t0 = time.monotonic()
+
+    def window_end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.monotonic()))
+            self._t0 = None
 
     def start(self):
         try:
@@ -76,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
     def stop(self) -> dict:
         if not self.proc:
@@ -88,7 +99,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # a line describes the ~50 ms before it arrived: keep those that arrived inside a window (or just after it)
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.06 for a, b in self.windows)]
+        if not self.windows:
+            inside = [ln for _, ln in self.lines]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -236,22 +251,24 @@ def run_b200(args):
     sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
                                   graph_unroll=args.graph_unroll, n_leaves=K)
     sp.prepare()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         sp.play_move()
     barrier()
 
     # ---- timed region 1: device-resident self-play (value) ------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = sp.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.window_begin()
     ev0.record()
     for _ in range(args.steps):
         sp.play_move()
     ev1.record()
     barrier()
+    sampler.window_end()
     ms = ev0.elapsed_time(ev1)
     launches = sp.total_launches() - l0
     sp.mcts.check_errors()
@@ -266,6 +283,7 @@ def run_b200(args):
     h_act = torch.empty(B, dtype=torch.uint8).pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.window_begin()
     e0.record()
     for _ in range(args.steps):
         d_me.copy_(h_me, non_blocking=True)
@@ -279,6 +297,7 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
     e1.record()
     barrier()
+    sampler.window_end()
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (value and e2e)
     h2d = 2 * B * 8
