@@ -55,10 +55,11 @@ class MCTSPlayer(ReversiPlayer):
     the deterministic hash pseudo-net is used (parity / tests)."""
 
     def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, size: int = 8, evaluator=None,
-                 salt: int = 0):
+                 salt: int = 0, n_leaves: int = 1):
         self.symbol = symbol  # 1 for X, -1 for O
         self.n_sims, self.size = int(n_sims), int(size)
-        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_REVERSI, board_size=size, c_puct=c_puct)
+        # n_leaves > 1: virtual-loss descents per iteration (n_sims must be a multiple); 1 = the sequential search
+        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_REVERSI, board_size=size, c_puct=c_puct, n_leaves=n_leaves)
         self.search = mcts.BatchedMCTS(self.pools, _make_evaluator(evaluator, net, salt), use_graph=False)
         self.last_counts = None
         self.last_policy = None
@@ -80,10 +81,11 @@ class MCTSPlayer(ReversiPlayer):
 class TicTacToeMCTSPlayer(Player):
     """MCTS player for the reference's tic-tac-toe loop (BASELINE config 1)."""
 
-    def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, evaluator=None, salt: int = 0):
+    def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, evaluator=None, salt: int = 0,
+                 n_leaves: int = 1):
         self.symbol = symbol
         self.n_sims = int(n_sims)
-        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_TTT, c_puct=c_puct)
+        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_TTT, c_puct=c_puct, n_leaves=n_leaves)
         self.search = mcts.BatchedMCTS(self.pools, _make_evaluator(evaluator, net, salt), use_graph=False)
         self.last_counts = None
         self.last_policy = None

@@ -161,3 +161,26 @@ def test_greedy_net_player_picks_best_legal_move():
     pl = GreedyNetPlayer(1, net.make_net("mlp", seed=1))
     mv = pl.get_move(b)
     assert mv in b.generate_possible_moves(1)
+
+
+@pytest.mark.parametrize("leaves", [2, 4])
+def test_ttt_mcts_players_with_virtual_loss_through_reference_loop(golden_mcts_vl, leaves):
+    """the drop-in player with n_leaves > 1 (single-tree wave kernels) in the reference's headless loop: per-ply root
+    visit counts and the winner equal the virtual-loss golden game (mcts_ref.MCTS.run_vl on the live reference)"""
+    from betazero_b200.boards import TicTacToeBoard
+    from betazero_b200.players import TicTacToeMCTSPlayer
+
+    g = golden_mcts_vl
+    p = f"ttt_game_s48_k{leaves}"
+    counts = []
+
+    class Rec(TicTacToeMCTSPlayer):
+        def get_move(self, board):
+            mv = super().get_move(board)
+            counts.append(self.last_counts.copy())
+            return mv
+
+    positions, winner = play_ttt_headless(TicTacToeBoard, Rec(1, n_sims=48, salt=1, n_leaves=leaves),
+                                          Rec(-1, n_sims=48, salt=1, n_leaves=leaves))
+    assert np.array_equal(np.stack(counts), g[p + "_counts"])
+    assert winner == int(g[p + "_winner"])
