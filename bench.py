@@ -205,11 +205,13 @@ def search_label(leaves):
 def workload_config(args):
     return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "leaves_per_iteration": args.leaves,
-            "search": search_label(args.leaves), "net": args.net, "hidden": args.hidden,
+            "search": search_label(args.leaves),
+            "evaluator": (f"policy/value MLP 128-{args.hidden}-{args.hidden}-{args.hidden}-(65+1), bf16, random init"
+                          if args.net == "mlp" else f"policy/value {args.net} (hidden {args.hidden}), bf16, random init"),
             "net_backend": (kernel_net_label(args.games * args.leaves) if getattr(args, "kernel_net", False)
                             else "PyTorch/cuBLASLt GEMMs"),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
-            "parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
+            "sharding": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
