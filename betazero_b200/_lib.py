@@ -77,13 +77,9 @@ SIGNATURES = {
     "bz_selfplay_advance": [_SP, _PP, ptr, ptr],
     "bz_reversi_symmetry": [ptr, ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
     "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
-    "bz_mlp_forward": [ptr] * 10 + [_I64, _INT, _INT, _INT, _INT, ptr],
-    "bz_mlp_forward_image": [ptr] * 7 + [_I64, ptr],
     "bz_mlp_forward_pair": [ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_pair_image_bytes": [],
     "bz_mlp_forward_pair2": [ptr, ptr, ptr, _I64, ptr],
-    "bz_mlp_forward_packed": [ptr, ptr, ptr, ptr, _I64, ptr],
-    "bz_mlp_weight_image_bytes": [],
     "bz_int32_microbench": [ptr, _INT, _INT, _INT, _INT, C.POINTER(C.c_int64), ptr],
 }
 
@@ -105,13 +101,19 @@ def load():
     if _lib is not None:
         return _lib
     path = os.environ.get("BETAZERO_B200_LIB") or _build.LIB  # override: kernel-variant experiments
-    try:
-        if path == _build.LIB and _build.needs_build():
-            _build.build()
-    except Exception as e:  # nvcc missing on a box that received a prebuilt .so is fine
-        if not os.path.exists(path):
-            raise BzError(f"libbetazero_b200.so is missing and could not be built ({e}); "
-                          "there is no CPU fallback") from e
+    if path == _build.LIB and _build.needs_build():
+        try:
+            _build._nvcc()
+        except RuntimeError as e:  # no compiler: a box that received a prebuilt .so may still run it
+            if not os.path.exists(path):
+                raise BzError(f"libbetazero_b200.so is missing and could not be built ({e}); "
+                              "there is no CPU fallback") from e
+            import warnings
+
+            warnings.warn("libbetazero_b200.so does not match the sources' hash and nvcc is not available to rebuild "
+                          "it: loading the existing library as is", RuntimeWarning)
+        else:
+            _build.build()  # a compile error in edited sources propagates: never run a stale library silently
     lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol

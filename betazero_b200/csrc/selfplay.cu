@@ -132,9 +132,19 @@ __global__ void __launch_bounds__(kThreads)
     // --- finished: score, flush the history to the replay buffer, restart the slot ----------------
     const int cm = __popcll(me), co = __popcll(opp);
     const int winner = ((cm > co) - (cm < co)) * (-player);  // absolute: +1 X, -1 O, 0 draw
-    unsigned long long rb = 0;
+    // counters[0] = rows COMMITTED to the replay buffer: a game reserves its rows with a compare-and-swap and takes
+    // nothing when it does not fit, so [0, counters[0]) never contains a row that no game wrote
+    unsigned long long rb = ~0ull;  // ~0: no room, the game is dropped (counted in counters[5])
     if (lane == 0) {
-        rb = atomicAdd(&S.counters[0], (unsigned long long)nrec);
+        unsigned long long cur = S.counters[0];
+        while (cur + (unsigned long long)nrec <= (unsigned long long)S.replay_cap) {
+            const unsigned long long seen = atomicCAS(&S.counters[0], cur, cur + (unsigned long long)nrec);
+            if (seen == cur) {
+                rb = cur;
+                break;
+            }
+            cur = seen;
+        }
         atomicAdd(&S.counters[1], 1ull);
         atomicAdd(&S.counters[3 + winner], 1ull);
         atomicAdd(&S.counters[6], 1ull);
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(kThreads)
     rb = __shfl_sync(kFull, rb, 0);
     __syncwarp();  // the record written above is visible to the copying lanes
     const int64_t h0 = (int64_t)s * S.max_plies;
-    if ((int64_t)rb + nrec <= S.replay_cap) {
+    if (rb != ~0ull) {
         for (int r = lane; r < nrec; r += 32) {
             S.rp_me[rb + r] = S.hist_me[h0 + r];
             S.rp_opp[rb + r] = S.hist_opp[h0 + r];

@@ -181,8 +181,8 @@ class FusedNetEvaluator:
         if not hasattr(net, "forward_raw"):
             raise TypeError("FusedNetEvaluator needs a net with forward_raw()")
         self.net = net
-        # None: the single-launch tcgen05 MLP kernel (bz_mlp_forward) when shape and batch allow, else
-        # the library GEMMs; True / "v2" / False force one path
+        # None: the single-launch tcgen05 MLP kernels (bz_mlp_forward_pair / _pair2) when the shape allows, else
+        # the library GEMMs; True / "pair" / "pair2" / False force one path
         self.use_kernel = use_kernel
         # programmatic dependent launch between the MLP kernel and the tree step kernel (process-wide
         # switch, results identical): on by default whenever the kernel path may be taken
@@ -319,8 +319,14 @@ class BatchedMCTS:
             raise ValueError(f"n_sims {n_sims} is not a multiple of the pools' n_leaves {K}")
         if self.pools.n_trees == 0:
             return
-        self.select()
         inner = n_sims // K - 1
+        if self.dirichlet_alpha > 0 and inner == 0:
+            # the noise perturbs the priors of the root that iteration 1 expands: a one-iteration search never uses it
+            raise ValueError(f"dirichlet_alpha > 0 needs at least two iterations (n_sims >= {2 * K}); got n_sims = {n_sims}")
+        if self.use_graph and self._graph is None and inner - (1 if self.dirichlet_alpha > 0 else 0) >= self.unroll:
+            raise RuntimeError("the CUDA graph is captured by prepare() (or search()) BEFORE reset(): capturing runs warm-up "
+                               "iterations on the pools and would clobber the roots just set")
+        self.select()
         if self.dirichlet_alpha > 0 and inner > 0:
             # iteration 1 expands the root; perturb its priors before the second descent
             self.evaluate()
@@ -329,8 +335,6 @@ class BatchedMCTS:
             self.select()
             inner -= 1
         if self.use_graph and inner >= self.unroll:
-            if self._graph is None:
-                raise RuntimeError("call prepare() before the first graph search")
             for _ in range(inner // self.unroll):
                 self._graph.replay()
                 self.launches += self._graph_launches

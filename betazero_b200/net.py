@@ -18,32 +18,6 @@ N_ACTIONS = 65
 TTT_ACTIONS = 9
 
 
-def pack_mlp_weights(weights, biases, split_halves: bool = True):
-    """Weight image + bias vector for ``bz_mlp_forward_packed``: every 128-row x 64-column block of a
-    layer (80 rows for the head) becomes one 16 KB unit laid out exactly as the kernel wants it in
-    shared memory (K-major SWIZZLE_128B: 16-byte chunk j of row r at chunk j ^ (r & 7)), units in
-    consumption order (layer, N-half, K slab).  ``weights``: [W1 [256,128], W2, W3 [256,256],
-    W_head [80,256]] bf16; returns (uint8 [24, 16384], float32 [848]).  ``split_halves=False`` keeps
-    all 256 rows of a K slab together (14 units of 32 KB: the image of ``bz_mlp_forward_image``)."""
-    units = []
-    for li, W in enumerate(weights):
-        N, K = W.shape
-        halves = 1 if (li == 3 or not split_halves) else 2
-        rows, ns = N // halves, K // 64
-        v = W.contiguous().view(halves, rows, ns, 8, 8).permute(0, 2, 1, 3, 4).contiguous()  # [h, s, r, j, e]
-        r = torch.arange(rows, device=W.device)[:, None]
-        j = torch.arange(8, device=W.device)[None, :]
-        src = (j ^ (r & 7))[None, None, :, :, None].expand(halves, ns, rows, 8, 8)
-        v = torch.gather(v, 3, src)  # position p of row r holds source chunk p ^ (r & 7)
-        u = v.reshape(halves * ns, rows * 64).view(torch.uint8)  # [units, rows*128 bytes]
-        pad = torch.zeros((u.shape[0], 16384 if split_halves else 32768), dtype=torch.uint8, device=W.device)
-        pad[:, : u.shape[1]] = u
-        units.append(pad)
-    image = torch.cat(units).contiguous()
-    bias = torch.cat([b.float().reshape(-1) for b in biases]).contiguous()
-    return image, bias
-
-
 def _swizzled_slabs(W: torch.Tensor) -> torch.Tensor:
     """[rows, K] bf16 -> uint8 [K/64 slabs, rows * 128 B]: K-major SWIZZLE_128B (16-byte chunk j of row r
     at chunk j ^ (r & 7) of its 128-byte row), the shared-memory image of a UMMA operand."""
@@ -95,24 +69,39 @@ class PolicyValueMLP(nn.Module):
     # -- inference fast paths -----------------------------------------------------------------------
     @torch.no_grad()
     def prepare_inference(self) -> None:
-        """(Re)build the fused policy+value head; call after every weight update."""
+        """(Re)build the fused policy+value head and the kernels' weight images; call after every weight update.
+
+        The buffers keep their ADDRESSES across calls (allocated once, refreshed with ``copy_``): a CUDA graph captured
+        by ``BatchedMCTS`` has the device pointers of the head / weight image baked into its kernel parameters, so a
+        refresh that re-allocated them would leave every graph replay reading the old (freed) weights."""
         A, H = self.n_actions, self.policy.in_features
         rows = max(self.raw_width, 80) if self.raw_width <= 80 else self.raw_width  # 80 = UMMA N of the fused kernel
         w = torch.zeros((rows, H), dtype=self.policy.weight.dtype, device=self.policy.weight.device)
         b = torch.zeros(rows, dtype=w.dtype, device=w.device)
         w[:A], w[A] = self.policy.weight, self.value.weight[0]
         b[:A], b[A] = self.policy.bias, self.value.bias[0]
-        self._head_full = (w.contiguous(), b.contiguous())
-        self._head = (w[: self.raw_width], b[: self.raw_width])
-        self._w = [m.weight.t() for m in (self.fc1, self.fc2, self.fc3)]
-        self._packed = None
+
+        def keep(name, new):
+            """store ``new`` under ``name``, in place when a buffer of the same shape / dtype / device exists"""
+            old = getattr(self, name, None)
+            if (isinstance(old, torch.Tensor) and old.shape == new.shape and old.dtype == new.dtype
+                    and old.device == new.device):
+                old.copy_(new)
+                return old
+            object.__setattr__(self, name, new.contiguous())
+            return getattr(self, name)
+
+        hw, hb = keep("_head_w", w), keep("_head_b", b)
+        self._head_full = (hw, hb)
+        self._head = (hw[: self.raw_width], hb[: self.raw_width])
+        self._w = [m.weight.t() for m in (self.fc1, self.fc2, self.fc3)]  # views of the parameters themselves
         if w.is_cuda and w.dtype == torch.bfloat16 and self.fc1.in_features == 128 and self.fc1.out_features == 256 \
                 and self.raw_width == 72:
-            ws = [self.fc1.weight, self.fc2.weight, self.fc3.weight, w[:80]]
-            bs = [self.fc1.bias, self.fc2.bias, self.fc3.bias, b[:80]]
-            self._packed = pack_mlp_weights(ws, bs)
-            self._image32 = pack_mlp_weights(ws, bs, split_halves=False)[0]
-            self._image_pair = pack_mlp_pair_image(ws, bs)
+            ws = [self.fc1.weight, self.fc2.weight, self.fc3.weight, hw[:80]]
+            bs = [self.fc1.bias, self.fc2.bias, self.fc3.bias, hb[:80]]
+            keep("_image_pair", pack_mlp_pair_image(ws, bs))
+        else:
+            self._image_pair = None
 
     def fused_kernel_ok(self, planes: torch.Tensor) -> bool:
         """the hand-written tcgen05 kernel covers exactly the Reversi shape in bf16 on a GPU"""
@@ -127,55 +116,34 @@ class PolicyValueMLP(nn.Module):
         ``fused=False``: 3 ``addmm+ReLU`` (cuBLASLt epilogue) + 1 head GEMM through PyTorch.
         ``fused="pair"``: the single-launch tcgen05 kernel on CTA pairs (``bz_mlp_forward_pair``: cta_group::2
         MMAs, each CTA keeps half of every weight matrix resident in shared memory);
-        ``fused=True``: the one-CTA-per-128-rows kernel with TMA weight streaming (``bz_mlp_forward_image``),
-        ``"ldgsts"`` the same kernel on the raw nn.Linear weights (``bz_mlp_forward``);
-        ``fused="v2"``: its warp-specialised, software-pipelined variant (``bz_mlp_forward_packed``).
         ``fused="pair2"``: the pair kernel with two ping-ponged tiles per pair (``bz_mlp_forward_pair2``).
-        ``fused=None`` (default) picks, for the supported shape, the pair kernel while one wave of CTA pairs
-        covers the batch (<= 74 x 128 rows) and the two-tile pair kernel above that; other shapes use the
-        library GEMMs.  All kernels give bit-identical outputs.  Measured on B200 per forward (graph, back
-        to back): 4096 rows pair 6.8 us / one-CTA 12.1 / cuBLASLt 11.8; 16 384 rows pair2 9.9 / 12.7 / 19.8;
-        65 536 rows pair2 34.5 / 45.5 / 52.4 (profiles/README.md)."""
+        ``fused=None`` / ``True`` picks, for the supported shape, the pair kernel while one wave of CTA pairs
+        covers the batch (<= 74 x 128 rows) and the two-tile pair kernel above that; ``None`` falls back to the
+        library GEMMs for other shapes, ``True`` raises.  Both kernels give bit-identical outputs.  Measured on
+        B200 per forward (graph, back to back): 4096 rows pair 6.8 us / cuBLASLt 11.8; 16 384 rows pair2 9.9 /
+        19.8; 65 536 rows pair2 34.5 / 52.4 (profiles/README.md)."""
         if self._head is None:
             self.prepare_inference()
         B = planes.shape[0]
-        if fused is None:  # auto: the hand-written kernels for the supported shape, at every batch size
-            fused = self.fused_kernel_ok(planes)
-            if fused and getattr(self, "_image_pair", None) is not None:
-                # one wave of CTA pairs with one 128-row tile each (lowest latency) up to 74 pairs; above that every
-                # pair ping-pongs two tiles (measured faster than cuBLASLt up to at least 131 072 rows)
-                fused = "pair" if B <= 74 * 128 else "pair2"
+        if fused is None or fused is True:
+            ok = self.fused_kernel_ok(planes) and getattr(self, "_image_pair", None) is not None
+            if fused is True and not ok:
+                raise RuntimeError("the tcgen05 MLP kernels cover only the bf16 128-256-256-256-(65+1) net on a GPU")
+            # one wave of CTA pairs with one 128-row tile each (lowest latency) up to 74 pairs; above that every
+            # pair ping-pongs two tiles (measured faster than cuBLASLt up to at least 131 072 rows)
+            fused = ("pair" if B <= 74 * 128 else "pair2") if ok else False
         if fused:
             from . import _lib
 
+            if fused not in ("pair", "pair2") or getattr(self, "_image_pair", None) is None:
+                raise RuntimeError(f"unknown / unavailable MLP kernel {fused!r}")
             if out is None:
                 out = torch.empty((B, self.raw_width), dtype=torch.bfloat16, device=planes.device)
-            if fused == "v2" and self._packed is not None:  # the pipelined kernel on the pre-swizzled weight image
-                img, bias = self._packed
-                L = _lib.load()
-                _lib.check(L.bz_mlp_forward_packed(_lib.dptr(planes.reshape(B, -1)), _lib.dptr(img), _lib.dptr(bias),
-                                                   _lib.dptr(out), B, _lib.stream_ptr()), "bz_mlp_forward_packed")
-                return out
-            hw, hb = self._head_full
             x = planes.reshape(B, -1)
             L = _lib.load()
-            if fused == "pair2" and getattr(self, "_image_pair", None) is not None:  # CTA pairs, two tiles per pair
-                _lib.check(L.bz_mlp_forward_pair2(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B,
-                                                  _lib.stream_ptr()), "bz_mlp_forward_pair2")
-                return out
-            if fused == "pair" and getattr(self, "_image_pair", None) is not None:  # CTA pairs, weights resident
-                _lib.check(L.bz_mlp_forward_pair(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B,
-                                                 _lib.stream_ptr()), "bz_mlp_forward_pair")
-                return out
-            if fused != "ldgsts" and getattr(self, "_image32", None) is not None:  # weights by cp.async.bulk (TMA)
-                _lib.check(L.bz_mlp_forward_image(_lib.dptr(x), _lib.dptr(self._image32), _lib.dptr(self.fc1.bias),
-                                                  _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.bias), _lib.dptr(hb),
-                                                  _lib.dptr(out), B, _lib.stream_ptr()), "bz_mlp_forward_image")
-                return out
-            _lib.check(L.bz_mlp_forward(_lib.dptr(x), _lib.dptr(self.fc1.weight), _lib.dptr(self.fc1.bias),
-                                        _lib.dptr(self.fc2.weight), _lib.dptr(self.fc2.bias), _lib.dptr(self.fc3.weight),
-                                        _lib.dptr(self.fc3.bias), _lib.dptr(hw), _lib.dptr(hb), _lib.dptr(out), B,
-                                        128, 256, hw.shape[0], self.raw_width, _lib.stream_ptr()), "bz_mlp_forward")
+            fn, name = ((L.bz_mlp_forward_pair2, "bz_mlp_forward_pair2") if fused == "pair2"
+                        else (L.bz_mlp_forward_pair, "bz_mlp_forward_pair"))
+            _lib.check(fn(_lib.dptr(x), _lib.dptr(self._image_pair), _lib.dptr(out), B, _lib.stream_ptr()), name)
             return out
         x = planes.reshape(B, -1).to(self.fc1.weight.dtype)
         x = torch._addmm_activation(self.fc1.bias, x, self._w[0])

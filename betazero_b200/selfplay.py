@@ -62,11 +62,14 @@ class BatchedSelfPlay:
         self._ref = C.byref(s)
         self._L = _lib.load()
         self.launches = 0
+        self._dropped_seen = 0  # counters[5] at the last drain (overflow is reported, never silent)
         _lib.check(self._L.bz_selfplay_init(self._ref, self.rank * self.n_games, _lib.stream_ptr()), "bz_selfplay_init")
         self.launches += 1
 
     # -- one lockstep ply for every game ----------------------------------------------------------
     def search(self) -> None:
+        if self.mcts.use_graph and self.mcts._graph is None and self.n_sims // self.pools.n_leaves - 1 >= self.mcts.unroll:
+            self.mcts.prepare()  # lazily, before the roots are set: play_move() works without an explicit prepare()
         self.mcts.reset(self.me, self.opp)
         self.mcts.run(self.n_sims)
 
@@ -91,7 +94,14 @@ class BatchedSelfPlay:
 
     def drain_replay(self) -> dict:
         """Returns the finished games' records (device tensors, copies) and empties the buffer."""
-        n = min(int(self.counters[0].item()), self.replay_cap)
+        c = self.counters.cpu().tolist()
+        n = min(int(c[0]), self.replay_cap)  # counters[0] counts committed rows only (a game that does not fit takes none)
+        if c[5] > self._dropped_seen:
+            import warnings
+
+            warnings.warn(f"replay buffer overflow: {c[5] - self._dropped_seen} records of finished games were dropped "
+                          f"(replay_cap {self.replay_cap}); drain more often or enlarge replay_cap", RuntimeWarning)
+            self._dropped_seen = c[5]
         out = {
             "me": self.rp_me[:n].clone(), "opp": self.rp_opp[:n].clone(),
             "pi": self.rp_pi[: n * N_ACTIONS].view(n, N_ACTIONS).clone(),

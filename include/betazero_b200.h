@@ -280,8 +280,9 @@ typedef struct bz_selfplay_state {
     int8_t *rp_z;
     int64_t *rp_game;
     int16_t *rp_ply;
-    /* device counters, uint64 [8]: 0 replay records written, 1 plies played, 2 O wins, 3 draws,
-     * 4 X wins, 5 records dropped (replay full), 6 games finished, 7 reserved */
+    /* device counters, uint64 [8]: 0 replay records COMMITTED (rows [0, counters[0]) of rp_* are all valid: a
+     * finished game reserves its rows atomically and takes none if it does not fit), 1 plies played, 2 O wins,
+     * 3 draws, 4 X wins, 5 records dropped (replay full), 6 games finished, 7 reserved */
     unsigned long long *counters;
 } bz_selfplay_state;
 
@@ -312,31 +313,21 @@ int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi
 
 /* Fused policy/value MLP inference (the network is the only dense contraction on the path and the
  * only tensor-core user): x bf16 [n, 128] canonical planes -> 128 -> 256 -> 256 -> 256 (ReLU) ->
- * head, all four layers in one tcgen05/TMEM kernel.  Architecture = the reference's TicTacToeNet
+ * head, all four layers in ONE tcgen05/TMEM kernel launch.  Architecture = the reference's TicTacToeNet
  * family (src/tic_tac_toe/SL/neural_networks.py:4-30, hidden 256 per SL/train.py:186) widened to
- * 8x8 with a value column.  Weights bf16 row-major [out, in] as torch.nn.Linear stores them; the
- * head is [80, 256] (65 policy rows, 1 value row, zero padding); biases bf16.  out: bf16
- * [n, 72] = BZ_PRIOR_LOGITS_BF16 input of bz_mcts_step.  Only this shape is supported
- * (in_features 128, hidden 256, head_rows 80, out_stride 72); anything else returns BZ_ERR_ARG. */
-int bz_mlp_forward(const void *x_bf16, const void *w1, const void *b1, const void *w2, const void *b2,
-                   const void *w3, const void *b3, const void *w_head, const void *b_head, void *out_bf16,
-                   int64_t n, int in_features, int hidden, int head_rows, int out_stride, bz_stream_t stream);
-
-/* bz_mlp_forward with the weights streamed by cp.async.bulk (TMA) instead of 16-byte LDGSTS copies:
- * weight_image32 = 14 units of 32 KB in (layer, K slab) order (layer 0: 2 slabs, layers 1-2: 4, head: 4
- * with 80 rows), each unit = all 256 weight rows of one 64-column K slab in the K-major SWIZZLE_128B
- * shared-memory layout (betazero_b200.net.pack_mlp_weights(..., split_halves=False)); biases bf16. */
-int bz_mlp_forward_image(const void *x_bf16, const void *weight_image32, const void *b1, const void *b2,
-                         const void *b3, const void *b_head, void *out_bf16, int64_t n, bz_stream_t stream);
-
-/* The same network on CTA pairs (clusters of 2, tcgen05.mma.cta_group::2): each pair owns 128 rows, each
+ * 8x8 with a value column.  out: bf16 [n, 72] (65 policy logits, the pre-tanh value, zero padding) =
+ * the BZ_PRIOR_LOGITS_BF16 input of bz_mcts_step.  Only this shape is supported.
+ *
+ * The kernels run on CTA pairs (clusters of 2, tcgen05.mma.cta_group::2): each pair owns 128 rows, each
  * CTA 64 of them and HALF of every weight matrix (the B operand of a pair MMA is split by output row), so
  * the whole net (180 KB per CTA) is resident in shared memory after five bulk copies issued at kernel
  * start.  weight_image_pair: bz_mlp_pair_image_bytes() bytes = [2 ranks][W1 half: 2 K slabs x 128 rows |
  * W2 half: 4 x 128 | W3 half: 4 x 128 | head half: 4 x 40 rows, 128 B per row, K-major SWIZZLE_128B |
- * biases float32 [256 + 256 + 256 + 80]] (betazero_b200.net.pack_mlp_pair_image builds it; rank r holds
- * rows r*128.. of the hidden layers and rows r*40.. of the 80-row head; both ranks carry all biases).
- * x / out as in bz_mlp_forward; results are bit-identical to it. */
+ * biases float32 [256 + 256 + 256 + 80]] (betazero_b200.net.pack_mlp_pair_image builds it from the
+ * torch.nn.Linear weights; rank r holds rows r*128.. of the hidden layers and rows r*40.. of the 80-row
+ * head; both ranks carry all biases).  x, weight_image_pair and out must be 16-byte aligned.
+ * (Round 1 also shipped three one-CTA-per-tile variants; they were slower at every batch size and now live,
+ * unbuilt, in profiles/experiments/mlp_onecta.cu.) */
 int bz_mlp_forward_pair(const void *x_bf16, const void *weight_image_pair, void *out_bf16, int64_t n,
                         bz_stream_t stream);
 int64_t bz_mlp_pair_image_bytes(void);
@@ -346,17 +337,6 @@ int64_t bz_mlp_pair_image_bytes(void);
  * layer.  Same weight image, x / out and results as bz_mlp_forward_pair. */
 int bz_mlp_forward_pair2(const void *x_bf16, const void *weight_image_pair, void *out_bf16, int64_t n,
                          bz_stream_t stream);
-
-/* The same network as a warp-specialised, software-pipelined kernel (MMA issuer / weight producer /
- * 16 epilogue warps; TMEM and activation double buffering, cp.async.bulk weight streaming).
- * weight_image: bz_mlp_weight_image_bytes() bytes = 24 units of 16 KB in consumption order
- * (layer 0: 2 N-halves x 2 K slabs; layers 1, 2: 2 x 4; head: 4 K slabs of 80 rows), every unit already
- * in the K-major SWIZZLE_128B shared-memory layout: 16-byte chunk j of weight row r sits at chunk
- * j ^ (r & 7) of its 128-byte row (betazero_b200.net.pack_mlp_weights builds it).
- * bias_f32: float32 [256 + 256 + 256 + 80].  x / out as in bz_mlp_forward. */
-int bz_mlp_forward_packed(const void *x_bf16, const void *weight_image, const void *bias_f32, void *out_bf16,
-                          int64_t n, bz_stream_t stream);
-int64_t bz_mlp_weight_image_bytes(void);
 
 /* INT32 issue-rate microbenchmark for the env roofline denominators.
  * variant 0: SHF + LOP3 chains, all on the ALU pipe (how 64-bit shifts/masks normally compile);

@@ -127,6 +127,32 @@ def test_headline_size_4096_trees_800_sims():
     assert np.array_equal(W[sample], r_W) and np.array_equal(P[sample], r_P)
 
 
+def test_headline_config_k4_wave_4096_trees_800_sims():
+    """The EXACT configuration bench.py times (BASELINE configs[3]): 4096 trees x 800 sims/move with 4 virtual-loss
+    descents per tree and iteration (step_wave_kernel<reversi, 8>, CUDA graph + fused step).  EVERY tree is checked
+    bit for bit (N, W, P of the root) against the C oracle's select_vl definition."""
+    from oracle import pyoracle as po
+
+    B, S, K = 4096, 800, 4
+    me_h, opp_h = po.playout_boards(B, seed=45)
+    s, cnt, pi, q = _search_vl(me_h, opp_h, S, 11, K)
+    live = po.terminal(me_h, opp_h)[0] == 0
+    # the K descents of the first iteration all end on the unexpanded root: S - K visits on the root edges
+    assert (cnt.sum(1)[live] == S - K).all() and (cnt.sum(1)[~live] == 0).all()
+    np.testing.assert_allclose(pi.sum(1)[live], 1.0, atol=1e-5)
+    mask = po.legal_mask(me_h, opp_h)
+    legal = ((mask[:, None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    assert (cnt[:, :64][~legal] == 0).all()
+    assert ((cnt[:, 64] > 0) == ((mask == 0) & live)).all()
+    assert (np.abs(q) <= 1.0).all()
+    sample = np.arange(B)  # every tree: the C oracle needs ~2 s for 4096 x 800 simulations
+    r_cnt, r_W, r_P, ctr = po.search_hash(me_h[sample], opp_h[sample], S, po.GAME_REVERSI, 8, 1.25, 11, leaves=K)
+    assert np.array_equal(cnt[sample], r_cnt)
+    W, P = _root_W_P(s)
+    assert np.array_equal(W[sample], r_W) and np.array_equal(P[sample], r_P)
+    np.testing.assert_allclose(q[sample], np.where(r_cnt > 0, r_W / np.maximum(r_cnt, 1), 0), rtol=RTOL, atol=0)
+
+
 def test_large_batch_uses_eight_lane_groups():
     """>= 8192 trees: the 4-trees-per-warp kernels are selected automatically; same answers"""
     from oracle import pyoracle as po
@@ -270,8 +296,8 @@ def test_hash_eval_kernel_matches_oracle():
 
 @pytest.mark.parametrize("group", GROUPS)
 def test_logits_mode_fused_softmax_and_tanh(group):
-    """BZ_PRIOR_LOGITS_BF16: the tree kernel does the legal-move softmax and tanh itself.  Floating
-    point with fast intrinsics, so tolerance-checked (1e-5 abs on priors) against numpy."""
+    """BZ_PRIOR_LOGITS_BF16: the tree kernel does the legal-move softmax and tanh itself (ex2.approx for the
+    softmax, libm tanhf for the value): priors and values within the north-star's 1e-5 RELATIVE of float64 numpy."""
     from betazero_b200 import env, mcts
     from oracle import pyoracle as po
 
@@ -308,11 +334,18 @@ def test_logits_mode_fused_softmax_and_tanh(group):
         l = logits[i, legal].astype(np.float64)
         p = np.exp(l - l.max())
         p /= p.sum()
-        np.testing.assert_allclose(P[i, legal], p, atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(P[i, legal], p, rtol=RTOL, atol=1e-12)  # 1e-5 RELATIVE (ex2.approx: 2^-22)
         assert P[i].sum() == pytest.approx(1.0, abs=1e-5) and N[i].sum() == 1
         a = int(np.argmax(N[i]))
-        # the visited child was expanded from the same logits row; its value tanh(l[65]) came back negated
-        assert W[i, a] == pytest.approx(-np.tanh(logits[i, 65]), abs=1e-5) or abs(W[i, a]) == 1.0 or W[i, a] == 0.0
+        # iteration 2 visited child `a`.  A finished game backs up its exact score; any other child was evaluated from
+        # the same logits row, and its value tanh(l[65]) came back negated: 1e-5 relative (north-star bound on Q)
+        cm, co, cerr = po.apply(me_h[i:i + 1], opp_h[i:i + 1], np.array([a], np.uint8))
+        assert not cerr[0]
+        c_over, c_win, _, _ = po.terminal(cm, co)
+        if c_over[0]:
+            assert W[i, a] == -float(c_win[0])
+        else:
+            np.testing.assert_allclose(W[i, a], -np.tanh(np.float64(logits[i, 65])), rtol=RTOL, atol=0)
 
 
 def test_fused_net_evaluator_agrees_with_parity_evaluator():

@@ -1,4 +1,4 @@
-"""GPU: the fused tcgen05 MLP kernel (bz_mlp_forward) against the PyTorch module it replaces.
+"""GPU: the fused tcgen05 MLP kernels (bz_mlp_forward_pair / _pair2) against the PyTorch module they replace.
 Floating point (bf16 inputs, fp32 accumulate, bf16 rounding after every layer), so the comparison
 is tolerance based: the two differ only in fp32 accumulation order."""
 import numpy as np
@@ -17,9 +17,8 @@ def _planes(B, seed):
     return torch.stack([(a == 1), (a == 2)], dim=1).reshape(B, 2, 8, 8).to(torch.bfloat16)
 
 
-# True: bz_mlp_forward_image (TMA weights); "ldgsts": bz_mlp_forward (raw weights); "v2": pipelined bz_mlp_forward_packed;
-# "pair": bz_mlp_forward_pair (cta_group::2, weights resident)
-@pytest.mark.parametrize("variant", [True, "ldgsts", "v2", "pair", "pair2"])
+# "pair": bz_mlp_forward_pair (cta_group::2, weights resident); "pair2": two ping-ponged tiles per pair; True: by batch size
+@pytest.mark.parametrize("variant", ["pair", "pair2", True])
 @pytest.mark.parametrize("B", [1, 7, 64, 65, 128, 129, 257, 1000, 4096])
 def test_fused_mlp_matches_torch_module(B, variant):
     from betazero_b200 import net
@@ -55,13 +54,13 @@ def test_fused_mlp_is_deterministic_and_row_independent():
 
     m = net.make_net("mlp", seed=1)
     x = _planes(300, 3)
-    a = m.forward_raw(x, fused=True).clone()
-    b = m.forward_raw(x, fused=True)
+    a = m.forward_raw(x, fused="pair").clone()
+    b = m.forward_raw(x, fused="pair")
     assert torch.equal(a, b)
-    c = m.forward_raw(x[37:38].contiguous(), fused=True)
+    c = m.forward_raw(x[37:38].contiguous(), fused="pair")
     assert torch.equal(c[0], a[37])  # a row's result does not depend on its batch
-    for other in ("v2", "ldgsts", "pair", "pair2"):
-        assert torch.equal(a, m.forward_raw(x, fused=other))  # same accumulation order (K ascending, fp32 in TMEM)
+    assert torch.equal(a, m.forward_raw(x, fused="pair2"))  # same accumulation order (K ascending, fp32 in TMEM)
+    assert torch.equal(c[0], m.forward_raw(x[37:38].contiguous(), fused="pair2")[0])
 
 
 def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
@@ -150,7 +149,7 @@ def test_pair_kernels_are_race_free_under_repetition():
     try:
         for B, mode in ((4096, "pair"), (16384, "pair2"), (777, "pair"), (9999, "pair2")):
             x = _planes(B, B + 1)
-            ref = m.forward_raw(x, fused=True).clone()
+            ref = m.forward_raw(x, fused="pair2" if mode == "pair" else "pair").clone()  # the OTHER kernel: bit-identical
             out = torch.empty_like(ref)
             for pdl in (False, True):
                 _lib.set_pdl(pdl)
@@ -164,3 +163,37 @@ def test_pair_kernels_are_race_free_under_repetition():
                 assert bad == 0 and torch.equal(out, ref), (B, mode, pdl)
     finally:
         _lib.set_pdl(False)
+
+
+@pytest.mark.parametrize("use_kernel", [None, False])
+@pytest.mark.parametrize("leaves", [1, 4])
+def test_refresh_after_weight_update_reaches_the_captured_graph(use_kernel, leaves):
+    """The [evaluate -> step] CUDA graph has the device pointers of the net's inference buffers (weight image, fused
+    head) baked in.  After a weight update + ``evaluator.refresh()`` -- what loop.py does every iteration -- a graph
+    replay must use the NEW weights: the buffers keep their addresses and are refreshed in place."""
+    from betazero_b200 import env, mcts, net
+    from oracle import pyoracle as po
+
+    B, n_sims = 256, 72
+    me_h, opp_h = po.playout_boards(B, seed=19)
+    me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
+    model = net.make_net("mlp", seed=3)
+    ev = mcts.FusedNetEvaluator(model, use_kernel=use_kernel)
+    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=leaves), ev, use_graph=True, graph_unroll=4)
+    cnt0 = s.search(me, opp, n_sims)[0].clone()
+    assert s._graph is not None
+    ptrs = (model._head_w.data_ptr(), model._head_b.data_ptr(),
+            model._image_pair.data_ptr() if model._image_pair is not None else 0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    with torch.no_grad():  # a "training step": every parameter changes in place
+        for prm in model.parameters():
+            prm.add_(torch.randn(prm.shape, device="cuda", generator=g).to(prm.dtype) * 0.3)
+    ev.refresh()
+    assert ptrs == (model._head_w.data_ptr(), model._head_b.data_ptr(),
+                    model._image_pair.data_ptr() if model._image_pair is not None else 0)
+    cnt1 = s.search(me, opp, n_sims)[0].clone()  # replays the graph captured BEFORE the update
+    fresh = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=leaves), mcts.FusedNetEvaluator(model, use_kernel=use_kernel),
+                             use_graph=False)
+    cnt2 = fresh.search(me, opp, n_sims)[0]
+    assert torch.equal(cnt1, cnt2)  # the graph saw the new weights
+    assert not torch.equal(cnt0, cnt1)  # and they really differ from the old ones

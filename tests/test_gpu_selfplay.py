@@ -36,11 +36,13 @@ def test_philox_matches_python_restatement():
     assert len(set(exp)) == 6
 
 
-@pytest.mark.parametrize("size,n_sims,leaves", [(4, 24, 1), (6, 16, 1), (4, 24, 4), (6, 16, 2)])
+@pytest.mark.parametrize("size,n_sims,leaves", [(4, 24, 1), (6, 16, 1), (4, 24, 4), (6, 16, 2),
+                                                (8, 32, 1), (8, 32, 4), (8, 64, 4), (8, 48, 2)])
 def test_deterministic_selfplay_equals_sequential_oracle(size, n_sims, leaves):
     """temp_plies = 0 (always the most visited move): every slot plays the same game as the oracle's
     sequential self_play_game in the order of the reference loop; check records, z and restart.
-    leaves > 1: the searches use virtual loss (wave mode on the GPU, MCTS.run_vl in the oracle)."""
+    leaves > 1: the searches use virtual loss (wave mode on the GPU, MCTS.run_vl in the oracle).
+    The 8x8 cases are the bench workload's board (BASELINE configs[3]): full 60-ply games, passes included."""
     from betazero_b200 import mcts, selfplay
 
     salt = 3
@@ -129,6 +131,35 @@ def test_full_games_recycle_slots_and_fill_replay():
     first = rp["ply"].cpu().numpy() == 0
     assert (me[first] == np.uint64((1 << 27) | (1 << 36))).all()
     assert len(np.unique(g0)) == st["games"]
+
+
+def test_replay_overflow_drops_whole_games_and_never_returns_unwritten_rows():
+    """replay_cap too small for the finished games: a game either gets all of its rows or none (counted as dropped);
+    drain_replay() warns and returns only rows some game really wrote"""
+    from betazero_b200 import mcts, selfplay
+
+    B, cap = 48, 100
+    sp = selfplay.BatchedSelfPlay(B, 8, mcts.HashEvaluator(2), board_size=4, temp_plies=30, seed=3, use_graph=False,
+                                  replay_cap=cap)
+    sp.rp_me.fill_(-1)  # poison: an unwritten row would show up as me == opp == all ones
+    sp.rp_opp.fill_(-1)
+    sp.rp_pi.fill_(float("nan"))
+    for _ in range(14):  # 4x4 games last <= 12 plies + passes
+        sp.play_move()
+    st = sp.stats()
+    assert st["games"] >= B and st["dropped"] > 0
+    assert st["replay_records"] <= cap
+    with pytest.warns(RuntimeWarning, match="replay buffer overflow"):
+        rp = sp.drain_replay()
+    n = rp["me"].numel()
+    assert n == st["replay_records"] and 0 < n <= cap
+    me, opp = rp["me"].cpu().numpy().view(np.uint64), rp["opp"].cpu().numpy().view(np.uint64)
+    assert not (me & opp).any()
+    np.testing.assert_allclose(rp["pi"].cpu().numpy().sum(1), 1.0, atol=1e-5)
+    game, ply = rp["game"].cpu().numpy(), rp["ply"].cpu().numpy()
+    for g in np.unique(game):  # whole games only: plies 0 .. k-1 of every game present
+        p = np.sort(ply[game == g])
+        assert np.array_equal(p, np.arange(len(p)))
 
 
 def test_symmetry_kernel_matches_reference_transform_list():
