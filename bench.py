@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the env-kernel / INT32 side measurements")
     ap.add_argument("--scale-games", type=int, default=65536,
                     help="also report throughput at this many games/GPU (0 = skip); not the headline value")
+    ap.add_argument("--no-iteration", action="store_true",
+                    help="skip extra.iteration (BASELINE configs[4]: self-play + replay all-gather + training + weight "
+                         "broadcast; the only part of the bench that moves bytes over NCCL)")
+    ap.add_argument("--iteration-plies", type=int, default=70, help="lockstep plies of extra.iteration (a game lasts ~60)")
     return ap.parse_args()
 
 
@@ -179,7 +183,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r2["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r2["steps"], "warmup": args.warmup, "ms_per_step": r2["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args),
+        # the same workload definition as the GPU arm, plus what this arm really timed: a bounded sample of its trees
+        "config": dict(workload_config(args), trees_timed=args.cpu_trees,
+                       timed_sample=f"{args.cpu_trees} of the {args.games} trees per step (bounded CPU sample)"),
         "cpu_baseline": {k: r2[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r2["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "positions_per_sec": r2["positions_per_sec"], "gpu_launches": 0,
@@ -203,8 +209,10 @@ def search_label(leaves):
 
 
 def workload_config(args):
-    return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3])",
-            "games_per_gpu": args.games, "sims_per_move": args.sims, "leaves_per_iteration": args.leaves,
+    return {"workload": f"reversi8x8 self-play, {args.sims} sims/move, {args.games} games/GPU (BASELINE configs[3]), "
+                        + (f"{args.leaves} virtual-loss descents per tree and iteration" if args.leaves > 1
+                           else "one descent per tree and iteration"),
+            "games_per_gpu": args.games, "trees_timed": args.games, "sims_per_move": args.sims, "leaves_per_iteration": args.leaves,
             "search": search_label(args.leaves),
             "evaluator": (f"policy/value MLP 128-{args.hidden}-{args.hidden}-{args.hidden}-(65+1), bf16, random init"
                           if args.net == "mlp" else f"policy/value {args.net} (hidden {args.hidden}), bf16, random init"),
@@ -306,60 +314,7 @@ def run_b200(args):
     d2h = B * 65 * 4 + B
 
     # ---- the dominant kernel (fused expand/backup + select + gather), timed launch by launch ------
-    # Preferred: CUDA events recorded INSIDE a replayed graph (event-record nodes, torch `external=True`): 16 iterations of
-    # [net, event, tree kernel, event] replayed on the deep-tree half of a search -- the interval holds the kernel and the
-    # ~1 us dependency latency of a graph edge, not an eager launch.  Fallback: eager launches behind a busy GPU.
-    n_iter = S // K - 1
-    step_kernel_ms, probe_kind = None, None
-    try:
-        pairs = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
-                 for _ in range(16)]
-        sp.mcts.reset(sp.me, sp.opp)
-        sp.mcts.select()
-        for _ in range(2):  # warm-up of the exact sequence that is captured
-            sp.mcts.evaluate()
-            sp.mcts.step()
-        pg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(pg):
-            for a, b in pairs:
-                sp.mcts.evaluate()
-                a.record()
-                sp.mcts.step()
-                b.record()
-        sp.mcts.reset(sp.me, sp.opp)
-        sp.mcts.select()
-        k_ms = []
-        done = 0
-        while done + 16 <= n_iter:
-            pg.replay()
-            done += 16
-            if done * 2 >= n_iter:  # deep-tree half
-                torch.cuda.synchronize()
-                k_ms += [a.elapsed_time(b) for a, b in pairs]
-        torch.cuda.synchronize()
-        if k_ms:
-            step_kernel_ms, probe_kind = sum(k_ms) / len(k_ms), "events inside a replayed CUDA graph"
-    except Exception as e:  # older torch without external events, or capture refused: fall back
-        print(f"graph-event probe unavailable ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
-    if step_kernel_ms is None:
-        sp.mcts.reset(sp.me, sp.opp)
-        sp.mcts.select()
-        evs = []
-        n_probe = min(n_iter, 400)
-        for i in range(n_probe):
-            sp.mcts.evaluate()
-            # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
-            # (eager launches are CPU-bound; without this the interval would include a launch gap)
-            torch.cuda._sleep(60_000)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            sp.mcts.step()
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        k_ms = [a.elapsed_time(b) for a, b in evs]
-        step_kernel_ms = sum(k_ms[len(k_ms) // 2:]) / max(1, len(k_ms) - len(k_ms) // 2)  # deep-tree half
-        probe_kind = "eager launches behind a busy GPU (includes ~4 us of launch latency)"
+    step_kernel_ms, net_kernel_ms, probe_kind = probe_iteration_split(torch, sp, S // K - 1)
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -370,6 +325,7 @@ def run_b200(args):
     value = total_sims / (ms * 1e-3)
     e2e_value = total_sims / (ms_e2e * 1e-3)
 
+    peak = None
     if rank == 0:
         peaks = {}
         try:
@@ -391,7 +347,10 @@ def run_b200(args):
                 # the issue rate of the chip, 148 SMs x 4 schedulers x 1 instruction/clk at the sampled SM clock
                 clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
                 peak_issue = 148 * 4 * clk
-                issue = {"bound": "issue", "warp_inst_per_launch": winst, "achieved": winst / (step_kernel_ms * 1e-3) / 1e9,
+                issue = {"bound": "issue", "warp_inst_per_launch": winst,
+                         "warp_inst_source": "profiles/traffic.json (static: ncu smsp__inst_executed.sum of this kernel at "
+                                             "this batch, not counted in this run)",
+                         "achieved": winst / (step_kernel_ms * 1e-3) / 1e9,
                          "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": winst / (step_kernel_ms * 1e-3) / peak_issue}
         except Exception:
             pass
@@ -409,24 +368,51 @@ def run_b200(args):
                                     f"step_wave_kernel<reversi, {32 // K} lanes per descent> (K7 + K5 + K6, {K} leaves per tree)"),
                          "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel_ms": step_kernel_ms,
-                         "kernel_ms_probe": probe_kind,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "profiles/traffic.json (static: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                           "one ncu --set full capture of this kernel, not measured in this run)",
+                         "kernel_ms": step_kernel_ms, "kernel_ms_probe": probe_kind,
+                         "net_kernel_ms": net_kernel_ms,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
                          "sims_per_launch": B * K, "issue": issue},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
             "selfplay": sp.stats(),
         }
+    else:
+        line = None
+
+    # ---- BASELINE configs[4]: one full AlphaZero iteration; EVERY rank takes part (replay all-gather + weight broadcast
+    # over NCCL are the only collectives of the design), rank 0 reports
+    pool_free = None
+    if not args.no_iteration:
+        del sp
+        torch.cuda.empty_cache()
+        pool_free = True
+        it_line = iteration_block(args, rank, world)
+        if rank == 0:
+            line.setdefault("extra", {})["iteration"] = it_line
+
+    if rank == 0:
         if not args.no_extra and world == 1:
-            line["extra"] = side_measurements(torch, env, peak)
-            del sp
-            torch.cuda.empty_cache()
+            if not pool_free:
+                del sp
+                torch.cuda.empty_cache()
+            ex = line.setdefault("extra", {})
+            ex.update(side_measurements(torch, env, peak))
+            if not args.no_cpu_baseline:
+                ex["env_cpu_baseline"] = env_cpu_baseline(ex)
             if hasattr(net, "forward_raw"):
-                line["extra"]["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
+                ex["full_game"] = full_game(torch, mcts, selfplay, net, args)
+                ex["depth_sweep"] = depth_sweep(torch, mcts, selfplay, netmod, args)
+                ex["config3_1024_trees_100_sims"] = config3(torch, mcts, selfplay, net, args)
+                ex["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
                 if K != 1:  # the strictly sequential search (one leaf per tree and iteration) on the same workload
-                    line["extra"]["one_leaf_per_iteration"] = alt_backend(torch, mcts, selfplay, net, args, leaves=1,
-                                                                          same_backend=True)
+                    ex["one_leaf_per_iteration"] = alt_backend(torch, mcts, selfplay, net, args, leaves=1, same_backend=True)
             if args.scale_games and args.scale_games != B:
-                line["extra"]["at_scale"] = at_scale(torch, mcts, selfplay, net, args, peak)
+                ex["at_scale"] = at_scale(torch, mcts, selfplay, net, args, args.scale_games, 1)
+                if K != 1:
+                    ex["at_scale_virtual_loss"] = [at_scale(torch, mcts, selfplay, net, args, g, K)
+                                                   for g in sorted({16384, args.scale_games}) if g != B]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay_sample(
                 args.cpu_trees, S, args.net, args.hidden, args.cpu_seconds, None, leaves=K).items()
@@ -435,6 +421,87 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def iteration_block(args, rank, world):
+    """extra.iteration: betazero_b200.loop.run_iteration at the bench's configuration (mirrors the reference's training
+    loop, SL/train.py:85-113, behind batched self-play).  Per-phase device times, gathered bytes, NCCL bus bandwidth."""
+    from betazero_b200 import loop
+
+    try:
+        la = loop.default_args(games=args.games, sims=args.sims, leaves=args.leaves, plies=args.iteration_plies,
+                               net=args.net, hidden=args.hidden, seed=1234)
+        st = loop.LoopState(la, rank, world)
+        out = loop.run_iteration(st, 0)
+        out["what"] = ("BASELINE configs[4]: lockstep self-play from the start positions (slots recycle as games end) -> "
+                       "replay drain + NCCL all-gather (one packed buffer) -> Adam steps on augmented batches -> "
+                       "NCCL weight broadcast + in-place refresh of the search's weight image")
+        del st
+        import torch
+
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        if world > 1:
+            raise  # a rank that skipped a collective would hang the others: fail loudly instead
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def probe_iteration_split(torch, sp, n_iter):
+    """Mean duration of the tree kernel and of the evaluator inside an MCTS iteration, over the deep-tree half of one search.
+    Preferred: CUDA events recorded INSIDE a replayed graph (event-record nodes, torch `external=True`): 16 iterations of
+    [net, event, tree kernel, event] -- an interval holds the kernel and the dependency latency of its graph edges, not
+    an eager launch.  Fallback: eager launches behind a busy GPU.  Returns (tree_ms, net_ms or None, probe description)."""
+    try:
+        pairs = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                 for _ in range(16)]
+        sp.mcts.reset(sp.me, sp.opp)
+        sp.mcts.select()
+        for _ in range(2):  # warm-up of the exact sequence that is captured
+            sp.mcts.evaluate()
+            sp.mcts.step()
+        pg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pg):
+            for a, b in pairs:
+                sp.mcts.evaluate()
+                a.record()
+                sp.mcts.step()
+                b.record()
+        sp.mcts.reset(sp.me, sp.opp)
+        sp.mcts.select()
+        k_ms, n_ms = [], []
+        done = 0
+        while done + 16 <= n_iter:
+            pg.replay()
+            done += 16
+            if done * 2 >= n_iter:  # deep-tree half
+                torch.cuda.synchronize()
+                k_ms += [a.elapsed_time(b) for a, b in pairs]
+                n_ms += [pairs[i][1].elapsed_time(pairs[i + 1][0]) for i in range(15)]
+        torch.cuda.synchronize()
+        if k_ms:
+            return sum(k_ms) / len(k_ms), sum(n_ms) / len(n_ms), "events inside a replayed CUDA graph"
+    except Exception as e:  # older torch without external events, or capture refused: fall back
+        print(f"graph-event probe unavailable ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
+    sp.mcts.reset(sp.me, sp.opp)
+    sp.mcts.select()
+    evs = []
+    n_probe = min(n_iter, 400)
+    for i in range(n_probe):
+        sp.mcts.evaluate()
+        # keep the GPU busy while the CPU enqueues the probed launch, so [a, b] holds the kernel only
+        # (eager launches are CPU-bound; without this the interval would include a launch gap)
+        torch.cuda._sleep(60_000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sp.mcts.step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = [a.elapsed_time(b) for a, b in evs]
+    half = k_ms[len(k_ms) // 2:] or [0.0]  # deep-tree half
+    return sum(half) / len(half), None, "eager launches behind a busy GPU (includes ~4 us of launch latency)"
+
 
 
 def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=False):
@@ -470,33 +537,196 @@ def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=Fals
         bzlib.set_pdl(False)
 
 
-def at_scale(torch, mcts, selfplay, net, args, hbm_peak):
-    """Same loop with many more concurrent games (the north-star asks for >= 4096 per GPU): the tree
-    kernel switches to 8-lane groups (4 trees per warp) and the latency chain is amortised."""
-    G, S = args.scale_games, args.sims
+def _timed_plies(torch, sp, warm, n):
+    for _ in range(warm):
+        sp.play_move()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        sp.play_move()
+    e1.record()
+    torch.cuda.synchronize()
+    sp.mcts.check_errors()
+    return e0.elapsed_time(e1) / n
+
+
+def at_scale(torch, mcts, selfplay, net, args, games, leaves):
+    """Same loop with many more concurrent games (the north-star asks for >= 4096 per GPU): with one leaf per iteration the
+    tree kernel switches to 8-lane groups (4 trees per warp); with virtual loss it stays in wave mode (a warp per tree)."""
+    G, S = games, args.sims
     try:
         evaluator = mcts.FusedNetEvaluator(net) if hasattr(net, "forward_raw") else mcts.NetEvaluator(net)
-        sp = selfplay.BatchedSelfPlay(G, S, evaluator, temp_plies=8, seed=99, graph_unroll=args.graph_unroll)
+        sp = selfplay.BatchedSelfPlay(G, S, evaluator, temp_plies=8, seed=99, graph_unroll=args.graph_unroll, n_leaves=leaves)
         sp.prepare()
-        for _ in range(2):
-            sp.play_move()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        n = 3
-        for _ in range(n):
-            sp.play_move()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
-        sp.mcts.check_errors()
+        ms = _timed_plies(torch, sp, 2, 3)
         st = sp.mcts.stats()
         d, b = st["mean_depth"], st["edges"] / max(1, st["sims"])
+        lanes = 32 // leaves if leaves in (2, 4) else (8 if G >= 32768 else (16 if G >= 8192 else 32))
         return {"games_per_gpu": G, "sims_per_sec": G * S / (ms * 1e-3), "positions_per_sec": G / (ms * 1e-3),
-                "ms_per_step": ms, "lanes_per_tree": 8 if G >= 32768 else (16 if G >= 8192 else 32), "leaves_per_iteration": 1, "mean_depth": d, "mean_children": b,
-                "pool_bytes": sp.pools.nbytes()}
+                "ms_per_step": ms, "lanes_per_descent": lanes, "leaves_per_iteration": leaves, "mean_depth": d,
+                "mean_children": b, "pool_bytes": sp.pools.nbytes()}
     except Exception as e:  # never let the side measurement break the headline line
+        return {"games_per_gpu": G, "leaves_per_iteration": leaves, "error": f"{type(e).__name__}: {e}"}
+    finally:
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(False)
+
+
+def full_game(torch, mcts, selfplay, net, args, plies=80, bucket=10):
+    """Whole games instead of the opening plies of the headline region: `plies` lockstep plies from the start position
+    (a Reversi game lasts ~60, so every slot finishes a game and restarts: slot recycling, replay flushes and the late-game
+    small trees are all inside the timed region).  Throughput over the whole run and per bucket of plies, with the tree
+    depth of the last search of each bucket."""
+    B, S, K = args.games, args.sims, args.leaves
+    try:
+        ev = mcts.FusedNetEvaluator(net, use_kernel=None if getattr(args, "kernel_net", False) else False)
+        sp = selfplay.BatchedSelfPlay(B, S, ev, temp_plies=8, seed=4321, graph_unroll=args.graph_unroll, n_leaves=K)
+        sp.prepare()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(plies // bucket + 1)]
+        depth = []
+        torch.cuda.synchronize()
+        marks[0].record()
+        for i in range(plies // bucket):
+            for _ in range(bucket):
+                sp.play_move()
+            marks[i + 1].record()
+            st = sp.mcts.stats()  # tiny D2H read between buckets (inside the timed run)
+            depth.append(st["mean_depth"])
+        torch.cuda.synchronize()
+        sp.mcts.check_errors()
+        n = (plies // bucket) * bucket
+        total_ms = marks[0].elapsed_time(marks[-1])
+        per = [marks[i].elapsed_time(marks[i + 1]) / bucket for i in range(plies // bucket)]
+        stats = sp.stats()
+        return {"plies": n, "games_per_gpu": B, "leaves_per_iteration": K, "ms_per_ply": total_ms / n,
+                "sims_per_sec": B * S * n / (total_ms * 1e-3), "positions_per_sec": B * n / (total_ms * 1e-3),
+                "games_finished": stats["games"], "replay_records": stats["replay_records"], "dropped": stats["dropped"],
+                "ply_buckets": [{"plies": f"{i * bucket}-{(i + 1) * bucket - 1}", "ms_per_ply": per[i],
+                                 "sims_per_sec": B * S / (per[i] * 1e-3), "mean_depth_last_search": depth[i]}
+                                for i in range(plies // bucket)],
+                "note": "sims counted as games x sims/move for every ply; slots whose game just ended search the start position"}
+    except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(False)
+
+
+def depth_sweep(torch, mcts, selfplay, netmod, args, scales=(1, 32, 128, 512)):
+    """Depth sensitivity: a random-init net has nearly flat priors, so its trees stay shallow (depth ~3).  A trained net has
+    peaked priors.  Multiplying the policy head by `scale` sharpens the priors of the SAME net; the search then goes
+    deeper and every extra tree level adds one dependent load round per descent.  Reports sims/s against mean depth."""
+    B, S, K = args.games, args.sims, args.leaves
+    out = []
+    try:
+        for scale in scales:
+            net = netmod.make_net(args.net, hidden=args.hidden, seed=0)
+            with torch.no_grad():
+                net.policy.weight.mul_(scale)
+                net.policy.bias.mul_(scale)
+            ev = mcts.FusedNetEvaluator(net, use_kernel=None if getattr(args, "kernel_net", False) else False)
+            sp = selfplay.BatchedSelfPlay(B, S, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll, n_leaves=K)
+            sp.prepare()
+            ms = _timed_plies(torch, sp, 6, 6)  # plies 6..11: mid-opening positions with ~8-10 legal moves
+            st = sp.mcts.stats()
+            out.append({"policy_logit_scale": scale, "mean_depth": st["mean_depth"],
+                        "mean_children": st["edges"] / max(1, st["sims"]), "ms_per_step": ms,
+                        "sims_per_sec": B * S / (ms * 1e-3)})
+            del sp, ev, net
+            torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return out + [{"error": f"{type(e).__name__}: {e}"}]
+    finally:
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(False)
+
+
+def config3(torch, mcts, selfplay, net, args, games=1024, sims=100, plies=70):
+    """BASELINE configs[2] / SURVEY 8d "Config 3": 1024 concurrent trees, 100 sims/move, random-init bf16 net, full games
+    from the start position; sims/s, positions/s and the time split env / tree (+ gather, fused into it) / net."""
+    K = args.leaves if sims % args.leaves == 0 else 1
+    try:
+        ev = mcts.FusedNetEvaluator(net, use_kernel=None if getattr(args, "kernel_net", False) else False)
+        sp = selfplay.BatchedSelfPlay(games, sims, ev, temp_plies=8, seed=3, graph_unroll=8, n_leaves=K)
+        sp.prepare()
+        ms = _timed_plies(torch, sp, 3, plies)
+        stats = sp.stats()
+        tree_ms, net_ms, probe = probe_iteration_split(torch, sp, sims // K - 1)
+        evs = []
+        for _ in range(20):  # the move / terminal / replay kernel of a ply, behind a busy GPU (no launch gap inside)
+            sp.search()
+            torch.cuda._sleep(60_000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sp.advance()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        env_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        iters = sims // K
+        return {"games": games, "sims_per_move": sims, "leaves_per_iteration": K, "plies": plies, "ms_per_ply": ms,
+                "sims_per_sec": games * sims / (ms * 1e-3), "positions_per_sec": games / (ms * 1e-3),
+                "games_finished": stats["games"],
+                "split_ms_per_ply": {"tree_select_expand_backup_gather": None if tree_ms is None else tree_ms * iters,
+                                     "net": None if net_ms is None else net_ms * iters,
+                                     "env_move_terminal_replay": env_ms,
+                                     "per_iteration": {"tree_kernel_ms": tree_ms, "net_kernel_ms": net_ms, "iterations": iters},
+                                     "probe": probe + "; env: events around bz_selfplay_advance behind a busy GPU"}}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(False)
+
+
+def env_cpu_baseline(extra, budget_boards=1 << 18):
+    """SURVEY 8d / BASELINE.md 4.1: the reference-style env on the host cores beside K1 / K2 -- the oracle port of
+    generate_possible_moves (64 x is_valid_move ray walks, reversi_board.py:25-41,87-88) and make_move (:43-59) on set A
+    (synthetic) and set B (reachable, random playouts) boards, one thread and all cores."""
+    import numpy as np
+
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    out = {"kind": "port", "cores": cores,
+           "what": "oracle.c grid + ray-walk restatement of ReversiBoard.generate_possible_moves + make_move (first legal move), "
+                   "OpenMP over boards"}
+    sets = {"set_a_synthetic": po.synthetic_boards(budget_boards, seed=0),
+            "set_b_playouts": po.playout_boards(budget_boards // 8, seed=0)}
+    try:
+        for name, (me, opp) in sets.items():
+            res = {"boards": int(me.size)}
+            for label, nt in (("1_thread", 1), (f"{cores}_threads", cores)):
+                po.set_num_threads(nt)
+                po.legal_mask(me[:1024], opp[:1024])  # warm-up
+                t0 = time.perf_counter()
+                mask = po.legal_mask(me, opp)
+                t1 = time.perf_counter()
+                low = mask & (~mask + np.uint64(1))
+                act = np.where(mask != 0, np.log2(np.maximum(low, 1).astype(np.float64)).astype(np.uint8), 64).astype(np.uint8)
+                t2 = time.perf_counter()
+                po.apply(me, opp, act)
+                t3 = time.perf_counter()
+                res[label] = {"legal_mask_boards_per_sec": me.size / (t1 - t0),
+                              "mask_plus_apply_boards_per_sec": me.size / ((t1 - t0) + (t3 - t2))}
+            out[name] = res
+        po.set_num_threads(cores)
+        k1 = extra.get("env_legal_mask", {}).get("boards_per_sec")
+        k12 = extra.get("env_step_first_legal", {}).get("boards_per_sec")
+        a = out["set_a_synthetic"][f"{cores}_threads"]
+        if k1 and k12:
+            out["gpu_over_cpu_all_cores"] = {"legal_mask": k1 / a["legal_mask_boards_per_sec"],
+                                             "mask_plus_apply": k12 / a["mask_plus_apply_boards_per_sec"]}
+        return out
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {e}"
+        return out
 
 
 def side_measurements(torch, env, hbm_peak):
@@ -534,17 +764,30 @@ def side_measurements(torch, env, hbm_peak):
     ops = env.int32_microbench(blocks, threads, iters)
     t3 = timed(lambda: env.int32_microbench(blocks, threads, iters), reps=3)
     peak_int = ops / t3 * 1e3
-    out["int32_peak"] = {"lane_ops_per_sec": peak_int, "ms": t3,
-                         "note": "SHF+LOP3 mix (ALU pipe), 8 independent chains/thread, 148x8 CTAs x 256 threads"}
-    # ALU-pipe utilisation and issued instructions per board come from the ncu capture committed in
-    # profiles/r1_env_kernels_raw.csv (sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,
-    # smsp__inst_executed.sum x 32 / boards); the issue rate below is measured live.
-    for key, inst, alu_frac in (("env_legal_mask", 216.6, 0.892), ("env_step_first_legal", 432.1, 0.935)):
-        out[key]["roofline"] = {"bound": "int32 ALU pipe", "frac": alu_frac, "frac_source": "ncu pipe_alu utilisation",
-                                "issued_inst_per_board": inst,
-                                "issued_lane_ops_per_sec": out[key]["boards_per_sec"] * inst,
-                                "measured_alu_pipe_peak_lane_ops_per_sec": peak_int,
-                                "note": "issued instructions include ~6 % IMAD/LDG/STG that do not use the ALU pipe"}
+    out["int32_peak"] = {"alu_pipe_thread_inst_per_sec": peak_int, "ms": t3,
+                         "note": "SHF+LOP3 mix (every instruction on the ALU pipe), 8 independent chains/thread, 148x8 CTAs x "
+                                 "256 threads; counted in thread-instructions, the unit of the fractions below"}
+    # INT32 roofline fraction, numerator and denominator both in ALU-pipe thread-instructions per second:
+    #   frac = boards/s (this run) x ALU-pipe instructions per board (static property of the binary) / ALU-pipe peak (this run)
+    inst = {}
+    try:
+        inst = json.load(open(os.path.join(ROOT, "profiles", "env_inst.json")))["kernels"]
+    except Exception:
+        pass
+    for key, kern in (("env_legal_mask", "legal_mask_kernel"), ("env_step_first_legal", "step_first_legal_kernel")):
+        k = inst.get(kern)
+        if not k:
+            continue
+        per_board = k.get("ncu_alu_pipe_inst_per_board") or k["alu_pipe_inst_per_board"]
+        rate = out[key]["boards_per_sec"] * per_board
+        out[key]["roofline"] = {"bound": "int32 ALU pipe", "frac": rate / peak_int, "unit": "ALU-pipe thread-inst/s",
+                                "achieved": rate, "peak": peak_int,
+                                "alu_pipe_inst_per_board": per_board,
+                                "alu_pipe_inst_per_board_source": "profiles/env_inst.json (static: executed ALU-pipe instructions "
+                                                                  "per board from the ncu capture r1_env_kernels_raw.csv; "
+                                                                  f"static SASS count {k['alu_pipe_inst_per_board']})",
+                                "frac_computed_from": "boards/s of this run x static instructions per board / ALU-pipe peak of "
+                                                      "this run"}
     return out
 
 

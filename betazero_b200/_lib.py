@@ -92,7 +92,7 @@ def lib_path() -> str:
     return _build.LIB
 
 
-ABI_VERSION = 2  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
+ABI_VERSION = 3  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
 
 
 def load():

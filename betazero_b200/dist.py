@@ -67,29 +67,68 @@ def broadcast_weights(module: torch.nn.Module, src: int = 0) -> int:
     return total
 
 
+def pack_records(local: dict) -> tuple[torch.Tensor, list]:
+    """Interleave a dict of per-record tensors (equal leading length n) into ONE uint8 [n, record_bytes] buffer
+    (fields in sorted key order, the record padded to a multiple of 16 bytes) + the layout to undo it."""
+    keys = sorted(local)
+    n = int(local[keys[0]].shape[0])
+    cols, layout, off = [], [], 0
+    for k in keys:
+        t = local[k].contiguous()
+        width = 1
+        for d in t.shape[1:]:
+            width *= int(d)
+        row_bytes = width * t.element_size()
+        layout.append((k, t.dtype, tuple(t.shape[1:]), off, row_bytes))
+        cols.append(t.reshape(n, width).view(torch.uint8).reshape(n, row_bytes))
+        off += row_bytes
+    pad = (-off) % 16
+    if pad:
+        cols.append(torch.zeros((n, pad), dtype=torch.uint8, device=cols[0].device))
+    return torch.cat(cols, dim=1).contiguous(), layout
+
+
+def unpack_records(buf: torch.Tensor, layout: list) -> dict:
+    n = int(buf.shape[0])
+    out = {}
+    for k, dt, shape, off, row_bytes in layout:
+        out[k] = buf[:, off:off + row_bytes].contiguous().view(dt).reshape((n,) + shape)
+    return out
+
+
+last_gather = {}  # bytes / record size of the most recent gather_replay (for the iteration report)
+
+
 def gather_replay(local: dict) -> dict:
     """All-gather variable-length replay shards (dict of tensors with equal leading length) to
-    every rank, ordered by (game id, ply) so the result does not depend on the rank layout."""
+    every rank, ordered by (game id, ply) so the result does not depend on the rank layout.
+
+    Two collectives in all: the shard lengths, then ONE all-gather of the records packed into a single byte buffer
+    (288 B per self-play record: me, opp, pi[65], z, game id, ply), padded to the longest shard; one host sync."""
     keys = sorted(local)
     n_local = int(local[keys[0]].shape[0])
+    last_gather.clear()
     if world_size() == 1:
         out = {k: local[k] for k in keys}
     else:
+        W = world_size()
         dev = local[keys[0]].device
-        counts = torch.zeros(world_size(), dtype=torch.int64, device=dev)
-        mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, mine)
-        n_max = int(counts.max().item())
-        out = {}
-        for k in keys:
-            t = local[k]
-            wire = t.to(torch.int32) if t.dtype in (torch.int16, torch.int8) else t  # gloo lacks some narrow types
-            pad = torch.zeros((n_max,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev)
-            pad[:n_local] = wire
-            buf = torch.empty((world_size() * n_max,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev)
-            dist.all_gather_into_tensor(buf, pad)
-            parts = [buf[r * n_max: r * n_max + int(counts[r].item())] for r in range(world_size())]
-            out[k] = torch.cat(parts).to(t.dtype)
+        packed, layout = pack_records(local)
+        rec = int(packed.shape[1])
+        counts = torch.zeros(W, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, torch.tensor([n_local], dtype=torch.int64, device=dev))
+        cnt = counts.cpu().tolist()  # the one host sync: the padded length must be known to size the buffer
+        n_max = max(cnt)
+        send = packed
+        if n_local < n_max:
+            send = torch.zeros((n_max, rec), dtype=torch.uint8, device=dev)
+            send[:n_local] = packed
+        buf = torch.empty((W * n_max, rec), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(buf, send)
+        rows = torch.cat([buf[r * n_max: r * n_max + cnt[r]] for r in range(W)]) if n_max else buf
+        out = unpack_records(rows, layout)
+        last_gather.update(record_bytes=rec, records=sum(cnt), wire_bytes_per_rank=n_max * rec,
+                           gathered_bytes=W * n_max * rec)
     if "game" in out and "ply" in out and out["game"].numel():
         order = torch.argsort(out["game"] * 1024 + out["ply"].to(torch.int64))
         out = {k: v[order] for k, v in out.items()}

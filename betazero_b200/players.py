@@ -123,3 +123,25 @@ class GreedyNetPlayer(ReversiPlayer):
         legal = np.array([(mask >> a) & 1 for a in range(64)], dtype=bool)
         a = int(np.argmax(np.where(legal, logits, -np.inf)))
         return a >> 3, a & 7
+
+
+class AIPlayer(ReversiPlayer):
+    """The reference's ``AIPlayer(path_to_model, symbol)`` (src/tic_tac_toe/players.py:77-98) for this engine's
+    checkpoints: built from a model FILE, plays the net's best legal move (:92-98).  The file is a state_dict
+    checkpoint written by ``betazero_b200.train.save_checkpoint`` (the reference pickles the whole module, :80 /
+    SL/train.py:214, which needs the defining source on the import path and arbitrary-code unpickling).
+    ``n_sims > 0`` puts the batched MCTS in front of the same net (what the AlphaZero loop's arena wants)."""
+
+    def __init__(self, path_to_model, symbol, n_sims: int = 0, size: int = 8, c_puct: float = 1.25, n_leaves: int = 1,
+                 device="cuda"):
+        from . import train
+
+        self.model = train.load_net(path_to_model, device=device)
+        self.symbol, self.size = symbol, int(size)
+        if n_sims > 0:
+            self._impl = MCTSPlayer(symbol, net=self.model, n_sims=n_sims, c_puct=c_puct, size=size, n_leaves=n_leaves)
+        else:
+            self._impl = GreedyNetPlayer(symbol, self.model, size=size)
+
+    def get_move(self, board):
+        return self._impl.get_move(board)

@@ -56,12 +56,24 @@ def train_step(net: torch.nn.Module, opt: torch.optim.Optimizer, planes, pi, z) 
     return {"loss": float(loss.detach()), "policy_loss": float(pl), "value_loss": float(vl)}
 
 
+def _arch_of(net: torch.nn.Module) -> dict:
+    """what load_net() needs to rebuild the module of a checkpoint"""
+    from . import net as netmod
+
+    if isinstance(net, netmod.PolicyValueMLP):
+        return {"kind": "mlp", "in_features": net.fc1.in_features, "hidden": net.fc1.out_features, "n_actions": net.n_actions}
+    if isinstance(net, netmod.PolicyValueResNet):
+        return {"kind": "resnet", "channels": net.stem[0].out_channels, "blocks": len(net.tower), "n_actions": net.p_fc.out_features}
+    return {"kind": type(net).__name__}
+
+
 def save_checkpoint(path: str, net: torch.nn.Module, opt: torch.optim.Optimizer | None = None, iteration: int = 0,
                     extra: dict | None = None) -> None:
     """state_dict checkpoint (loads with weights_only=True), unlike the reference's whole-module
-    pickle (train.py:204-214) which torch >= 2.6 refuses to load by default."""
+    pickle (train.py:204-214) which torch >= 2.6 refuses to load by default.  The architecture is stored beside the
+    weights so that a player can be built from the path alone (AIPlayer(path_to_model, symbol), players.py:77-81)."""
     torch.save({"model": net.state_dict(), "optimizer": opt.state_dict() if opt is not None else None,
-                "iteration": int(iteration), "extra": extra or {}}, path)
+                "iteration": int(iteration), "arch": _arch_of(net), "extra": extra or {}}, path)
 
 
 def load_checkpoint(path: str, net: torch.nn.Module, opt: torch.optim.Optimizer | None = None) -> int:
@@ -69,4 +81,23 @@ def load_checkpoint(path: str, net: torch.nn.Module, opt: torch.optim.Optimizer 
     net.load_state_dict(ck["model"])
     if opt is not None and ck.get("optimizer") is not None:
         opt.load_state_dict(ck["optimizer"])
+    if hasattr(net, "prepare_inference") and getattr(net, "_head", None) is not None:
+        net.prepare_inference()  # refresh the fused inference buffers in place (captured graphs keep working)
     return int(ck.get("iteration", 0))
+
+
+def load_net(path: str, device="cuda", dtype=torch.bfloat16) -> torch.nn.Module:
+    """Rebuild the module a checkpoint was saved from (its ``arch`` record) and load the weights: the equivalent of the
+    reference's ``torch.load(path_to_model)`` (players.py:80) for state_dict checkpoints."""
+    from . import net as netmod
+
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    arch = ck.get("arch") or {}
+    if arch.get("kind") == "mlp":
+        m = netmod.PolicyValueMLP(arch["in_features"], arch["hidden"], arch["n_actions"])
+    elif arch.get("kind") == "resnet":
+        m = netmod.PolicyValueResNet(arch["channels"], arch["blocks"], arch["n_actions"])
+    else:
+        raise ValueError(f"checkpoint {path!r} does not describe a known architecture: {arch!r}")
+    m.load_state_dict(ck["model"])
+    return m.to(device=device, dtype=dtype).eval()

@@ -32,7 +32,7 @@ extern "C" {
 #define BZ_OK 0
 #define BZ_ERR_ARG (-1)
 #define BZ_ERR_UNALIGNED (-2)
-#define BZ_ABI_VERSION 2
+#define BZ_ABI_VERSION 3
 
 #define BZ_REVERSI_ACTIONS 65
 #define BZ_TTT_ACTIONS 9
@@ -45,7 +45,7 @@ typedef void *bz_stream_t; /* cudaStream_t */
 
 int bz_abi_version(void);
 
-/* Process-wide switch for programmatic dependent launch between bz_mcts_step and bz_mlp_forward
+/* Process-wide switch for programmatic dependent launch between bz_mcts_step and bz_mlp_forward_pair*
  * (each kernel's prologue overlaps the other's tail; both wait on griddepcontrol before reading
  * the other's output).  Returns the previous setting.  Off by default. */
 int bz_set_pdl(int enable);
