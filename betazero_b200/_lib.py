@@ -68,6 +68,7 @@ SIGNATURES = {
     "bz_mcts_gather": [_PP, ptr],
     "bz_mcts_expand_backup": [_PP, ptr, ptr, ptr],
     "bz_mcts_step": [_PP, ptr, ptr, ptr],
+    "bz_mcts_search_fused": [_PP, ptr, ptr, _INT, ptr],
     "bz_mcts_root_policy": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_root_edges": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_best_action": [_PP, ptr, ptr],
@@ -92,7 +93,7 @@ def lib_path() -> str:
     return _build.LIB
 
 
-ABI_VERSION = 3  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
+ABI_VERSION = 4  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
 
 
 def load():

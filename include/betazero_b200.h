@@ -32,7 +32,7 @@ extern "C" {
 #define BZ_OK 0
 #define BZ_ERR_ARG (-1)
 #define BZ_ERR_UNALIGNED (-2)
-#define BZ_ABI_VERSION 3
+#define BZ_ABI_VERSION 4
 
 #define BZ_REVERSI_ACTIONS 65
 #define BZ_TTT_ACTIONS 9
@@ -223,6 +223,20 @@ int bz_mcts_expand_backup(const bz_tree_pools *pools, const void *eval_out, cons
 
 /* K7+K5+K6 in one launch: finish iteration i with the evaluator's output, start iteration i+1. */
 int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *value, bz_stream_t stream);
+
+/* The whole search of one move in ONE launch: K5 (select), then n_iterations x [the policy/value MLP on the pending
+ * leaves, K7 (expand + backup), K5 + K6 for the next iteration (not after the last)] -- the sequence
+ * bz_mcts_select, n x [bz_mlp_forward_pair*, bz_mcts_step / bz_mcts_expand_backup] computes, with bit-identical trees.
+ * Player.get_move's search loop (reversi_players.py:5-8) without a kernel boundary per iteration: a CTA pair owns 56
+ * trees in two islands; while one island's leaves are in the net (tcgen05 cta_group::2, the weight image of
+ * bz_mlp_forward_pair resident in shared memory for the whole search, the leaf planes written from registers into the
+ * A operand) the other island's warps walk their trees.
+ * Shape: Reversi, n_leaves == 4 in wave mode (group_lanes 0 or 32), prior_mode BZ_PRIOR_LOGITS_BF16 with
+ * eval_stride == 72, n_trees <= 148 * 28 = 4144 (BZ_ERR_ARG otherwise: use the per-iteration entry points).
+ * eval_out: [4 * n_trees, 72] bf16 scratch (the net's rows of the last iteration on return); leaf_planes is not
+ * written.  n_iterations = simulations per tree / 4. */
+int bz_mcts_search_fused(const bz_tree_pools *pools, const void *weight_image_pair, void *eval_out, int n_iterations,
+                         bz_stream_t stream);
 
 /* Root exploration noise (AlphaZero self-play; OFF in every parity test): for each tree whose
  * root is expanded, P[e] <- (1 - eps) * P[e] + eps * noise[a_e] / sum over the root's edges of
