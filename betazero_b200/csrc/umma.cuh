@@ -53,6 +53,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+// The same wait for warps that may wait for microseconds beside working warps (the one-launch search): try_wait with a
+// suspend-time hint parks the thread in hardware instead of spinning through the issue slots of the SM sub-partition
+// (a plain try_wait loop was 36 % of all instructions issued by search_fused_kernel).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -221,8 +221,13 @@ class BatchedMCTS:
     """
 
     def __init__(self, pools: TreePools, evaluator, use_graph: bool = True, graph_unroll: int = 16, fused: bool = True,
-                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, noise_seed: int = 0):
+                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, noise_seed: int = 0,
+                 one_launch: bool | None = None):
         self.pools, self.evaluator = pools, evaluator
+        # one_launch: run the whole search of a move in ONE kernel (bz_mcts_search_fused) when the shape allows --
+        # Reversi, 4 leaves per iteration in wave mode, the bf16 MLP through its tcgen05 kernel path, at most 4144 trees.
+        # None = whenever possible; False = always the per-iteration kernels; True = raise if the shape does not fit.
+        self._one_launch_arg = one_launch
         # root exploration noise (self-play only; 0 = off, which every parity test uses)
         self.dirichlet_alpha, self.dirichlet_eps = float(dirichlet_alpha), float(dirichlet_eps)
         self._noise_gen = torch.Generator(device=pools.device).manual_seed(int(noise_seed)) if dirichlet_alpha > 0 else None
@@ -242,6 +247,35 @@ class BatchedMCTS:
         # Programmatic dependent launch is a property of THIS search's kernel sequence: only an evaluator that puts a
         # kernel between two step kernels (FusedNetEvaluator) may ask for it; applied before every launch / capture.
         self._pdl = bool(getattr(evaluator, "pdl", False))
+
+    # -- the one-launch search ------------------------------------------------------------------
+    ONE_LAUNCH_MAX_TREES = 148 * 28
+
+    def one_launch_ok(self) -> bool:
+        """bz_mcts_search_fused covers this search (same trees, bit for bit, as the per-iteration kernels)."""
+        p, ev = self.pools, self.evaluator
+        net = getattr(ev, "net", None)
+        return (isinstance(ev, FusedNetEvaluator) and ev.use_kernel is not False and getattr(ev, "own_launches", 0) == 1
+                and getattr(net, "_image_pair", None) is not None and self.fused
+                and p.game == GAME_REVERSI and p.n_leaves == 4 and p.group_lanes in (0, 32)
+                and p.prior_mode == PRIOR_LOGITS_BF16 and p.eval_stride == 72 and 0 < p.n_trees <= self.ONE_LAUNCH_MAX_TREES)
+
+    @property
+    def one_launch(self) -> bool:
+        if self._one_launch_arg is False:
+            return False
+        ok = self.one_launch_ok()
+        if self._one_launch_arg and not ok:
+            raise RuntimeError("one_launch=True, but bz_mcts_search_fused does not cover this search (it needs Reversi, "
+                               "n_leaves = 4 in wave mode, the bf16 MLP kernel path and at most 4144 trees)")
+        return ok
+
+    def search_one_launch(self, n_iterations: int) -> None:
+        """select, then n_iterations x [net, expand + backup, select (not after the last)] in one kernel."""
+        _lib.check(self._L.bz_mcts_search_fused(self.pools._ref, _lib.dptr(self.evaluator.net._image_pair),
+                                                _lib.dptr(self.prior_w), int(n_iterations), _lib.stream_ptr()),
+                   "bz_mcts_search_fused")
+        self.launches += 1
 
     # -- single kernels ------------------------------------------------------------------------
     def reset(self, root_me: torch.Tensor, root_opp: torch.Tensor) -> None:
@@ -320,6 +354,19 @@ class BatchedMCTS:
         if self.pools.n_trees == 0:
             return
         inner = n_sims // K - 1
+        if self.one_launch:
+            if self.dirichlet_alpha > 0:
+                if inner == 0:
+                    raise ValueError(f"dirichlet_alpha > 0 needs at least two iterations (n_sims >= {2 * K}); got n_sims = {n_sims}")
+                # iteration 1 expands the root with the per-iteration kernels; its priors are perturbed before the rest
+                self.select()
+                self.evaluate()
+                self.expand_backup()
+                self.add_root_noise()
+                self.search_one_launch(inner)
+            else:
+                self.search_one_launch(inner + 1)
+            return
         if self.dirichlet_alpha > 0 and inner == 0:
             # the noise perturbs the priors of the root that iteration 1 expands: a one-iteration search never uses it
             raise ValueError(f"dirichlet_alpha > 0 needs at least two iterations (n_sims >= {2 * K}); got n_sims = {n_sims}")
@@ -358,12 +405,12 @@ class BatchedMCTS:
 
     def prepare(self) -> None:
         """Capture the CUDA graph (clobbers the pending leaf state: call before reset())."""
-        if self.use_graph and self._graph is None and self.pools.n_trees > 0:
+        if self.use_graph and self._graph is None and self.pools.n_trees > 0 and not self.one_launch:
             self._capture()
 
     def search(self, root_me: torch.Tensor, root_opp: torch.Tensor, n_sims: int, check: bool = True):
         """Fresh search from the given roots.  Returns (visit_counts, pi, q) device tensors."""
-        if self.use_graph and self._graph is None and n_sims // self.pools.n_leaves - 1 >= self.unroll:
+        if self.use_graph and self._graph is None and n_sims // self.pools.n_leaves - 1 >= self.unroll and not self.one_launch:
             self.prepare()
         self.reset(root_me, root_opp)
         self.run(n_sims)

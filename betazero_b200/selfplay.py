@@ -25,7 +25,8 @@ class BatchedSelfPlay:
     def __init__(self, n_games: int, n_sims: int, evaluator, board_size: int = 8, c_puct: float = 1.25,
                  temp_plies: int = 0, seed: int = 0, replay_cap: int | None = None, rank: int = 0, world: int = 1,
                  arena_units: int | None = None, use_graph: bool = True, graph_unroll: int = 16,
-                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, n_leaves: int = 1, device="cuda"):
+                 dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, n_leaves: int = 1, device="cuda",
+                 one_launch: bool | None = None):
         self.n_games, self.n_sims, self.board_size = int(n_games), int(n_sims), int(board_size)
         self.rank, self.world = int(rank), int(world)
         self.device = torch.device(device)
@@ -33,7 +34,7 @@ class BatchedSelfPlay:
                                n_leaves=n_leaves, device=device)
         self.mcts = BatchedMCTS(self.pools, evaluator, use_graph=use_graph, graph_unroll=graph_unroll,
                                 dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps,
-                                noise_seed=seed * 7919 + rank)
+                                noise_seed=seed * 7919 + rank, one_launch=one_launch)
         self.max_plies = 128
         B, H = max(self.n_games, 1), max(self.n_games, 1) * self.max_plies
         self.replay_cap = int(replay_cap if replay_cap is not None else B * 2 * self.max_plies)
@@ -68,7 +69,8 @@ class BatchedSelfPlay:
 
     # -- one lockstep ply for every game ----------------------------------------------------------
     def search(self) -> None:
-        if self.mcts.use_graph and self.mcts._graph is None and self.n_sims // self.pools.n_leaves - 1 >= self.mcts.unroll:
+        if (self.mcts.use_graph and self.mcts._graph is None and not self.mcts.one_launch
+                and self.n_sims // self.pools.n_leaves - 1 >= self.mcts.unroll):
             self.mcts.prepare()  # lazily, before the roots are set: play_move() works without an explicit prepare()
         self.mcts.reset(self.me, self.opp)
         self.mcts.run(self.n_sims)

@@ -179,7 +179,7 @@ def test_refresh_after_weight_update_reaches_the_captured_graph(use_kernel, leav
     me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
     model = net.make_net("mlp", seed=3)
     ev = mcts.FusedNetEvaluator(model, use_kernel=use_kernel)
-    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=leaves), ev, use_graph=True, graph_unroll=4)
+    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=leaves), ev, use_graph=True, graph_unroll=4, one_launch=False)
     cnt0 = s.search(me, opp, n_sims)[0].clone()
     assert s._graph is not None
     ptrs = (model._head_w.data_ptr(), model._head_b.data_ptr(),
@@ -193,7 +193,7 @@ def test_refresh_after_weight_update_reaches_the_captured_graph(use_kernel, leav
                     model._image_pair.data_ptr() if model._image_pair is not None else 0)
     cnt1 = s.search(me, opp, n_sims)[0].clone()  # replays the graph captured BEFORE the update
     fresh = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=leaves), mcts.FusedNetEvaluator(model, use_kernel=use_kernel),
-                             use_graph=False)
+                             use_graph=False, one_launch=False)
     cnt2 = fresh.search(me, opp, n_sims)[0]
     assert torch.equal(cnt1, cnt2)  # the graph saw the new weights
     assert not torch.equal(cnt0, cnt1)  # and they really differ from the old ones
