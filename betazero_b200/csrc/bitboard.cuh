@@ -196,6 +196,17 @@ __device__ __forceinline__ void group_legal_masks(unsigned gmask, int gl, uint64
     }
 }
 
+// The same for G == 8 with the opponent's mask computed only when some group of the warp needs it: the caller uses
+// mask_opp only where mask_me == 0 (pass or game over?), which few positions are, and `want` is false for groups whose
+// result is discarded.  Every lane of the warp must call this together; mask_opp is valid where want && mask_me == 0.
+__device__ __forceinline__ void group8_legal_masks_lazy(unsigned gmask, int gl, uint64_t me, uint64_t opp, uint64_t cells,
+                                                        bool want, uint64_t &mask_me, uint64_t &mask_opp) {
+    const uint64_t empty = ~(me | opp) & cells;
+    mask_me = group_or64(gmask, dir_moves(gl, me, opp)) & empty;
+    mask_opp = 0;
+    if (__any_sync(0xFFFFFFFFu, want && mask_me == 0)) mask_opp = group_or64(gmask, dir_moves(gl, opp, me)) & empty;
+}
+
 // ---- tic-tac-toe: 9-bit boards, bit = row*3 + col --------------------------------------------
 __device__ __forceinline__ bool ttt_has_line(unsigned b) {
     // rows 0x007 0x038 0x1C0, columns 0x049 0x092 0x124, diagonals 0x111 0x054

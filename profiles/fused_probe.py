@@ -10,7 +10,7 @@ me, opp, _ = env.reversi_init(B)
 L = _lib.load()
 
 def searcher():
-    s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=4), mcts.FusedNetEvaluator(model), graph_unroll=16)
+    s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=4), mcts.FusedNetEvaluator(model), graph_unroll=16, one_launch=False)
     s.prepare()
     return s
 
