@@ -216,8 +216,12 @@ def workload_config(args):
             "search": search_label(args.leaves),
             "evaluator": (f"policy/value MLP 128-{args.hidden}-{args.hidden}-{args.hidden}-(65+1), bf16, random init"
                           if args.net == "mlp" else f"policy/value {args.net} (hidden {args.hidden}), bf16, random init"),
-            "net_backend": (kernel_net_label(args.games * args.leaves) if getattr(args, "kernel_net", False)
+            "net_backend": (("inside search_fused_kernel: tcgen05 cta_group::2 on CTA pairs, weight image resident in shared "
+                             "memory for the whole move, leaf planes written from registers into the A operand")
+                            if getattr(args, "one_launch", False) else
+                            kernel_net_label(args.games * args.leaves) if getattr(args, "kernel_net", False)
                             else "PyTorch/cuBLASLt GEMMs"),
+            "launches_per_move": (3 if getattr(args, "one_launch", False) else None),
             "l2_policy": "working set > L2: tree pools of one rank span GBs (no flush needed)",
             "sharding": f"games sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -261,6 +265,7 @@ def run_b200(args):
     sp = selfplay.BatchedSelfPlay(B, S, evaluator, temp_plies=8, seed=1234, rank=rank, world=world,
                                   graph_unroll=args.graph_unroll, n_leaves=K)
     sp.prepare()
+    args.one_launch = bool(sp.mcts.one_launch)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -313,8 +318,15 @@ def run_b200(args):
     h2d = 2 * B * 8
     d2h = B * 65 * 4 + B
 
-    # ---- the dominant kernel (fused expand/backup + select + gather), timed launch by launch ------
-    step_kernel_ms, net_kernel_ms, probe_kind = probe_iteration_split(torch, sp, S // K - 1)
+    # ---- the dominant kernel, timed launch by launch ------
+    one_launch = bool(sp.mcts.one_launch)
+    if one_launch:
+        # search_fused_kernel: the whole search of a ply (tree kernels + net) is ONE launch
+        step_kernel_ms, net_kernel_ms, probe_kind = probe_one_launch(torch, sp, S // K), None, \
+            "CUDA events around each of 8 launches (one per ply) on the launching stream"
+    else:
+        # fused expand/backup + select + gather of one iteration
+        step_kernel_ms, net_kernel_ms, probe_kind = probe_iteration_split(torch, sp, S // K - 1)
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -336,12 +348,19 @@ def run_b200(args):
         d = tstats["mean_depth"]
         bmean = tstats["edges"] / max(1, tstats["sims"])  # edges created per iteration ~ mean children of a new node
         bytes_per_sim = 28 * d + 12 * d * bmean + 13 * bmean + 312
-        achieved = bytes_per_sim * B * K / (step_kernel_ms * 1e-3) / 1e9  # B * K simulations per launch
-        traffic, issue = None, None
+        sims_per_launch = B * S if one_launch else B * K
+        achieved = bytes_per_sim * sims_per_launch / (step_kernel_ms * 1e-3) / 1e9
+        traffic, issue, static_note = None, None, None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof.get("mcts_step_dram_bytes_per_launch" if K == 1 else f"mcts_step_wave{K}_dram_bytes_per_launch")
-            winst = prof.get("mcts_step_warp_inst_per_launch" if K == 1 else f"mcts_step_wave{K}_warp_inst_per_launch")
+            if one_launch:
+                same = B == 4096 and S == 800
+                traffic = prof.get("search_fused_dram_bytes_per_launch") if same else None
+                winst = prof.get("search_fused_warp_inst_per_launch") if same else None
+                static_note = prof.get("search_fused_note")
+            else:
+                traffic = prof.get("mcts_step_dram_bytes_per_launch" if K == 1 else f"mcts_step_wave{K}_dram_bytes_per_launch")
+                winst = prof.get("mcts_step_warp_inst_per_launch" if K == 1 else f"mcts_step_wave{K}_warp_inst_per_launch")
             if winst and B == 4096:
                 # second roofline of the same kernel: warp instructions issued (ncu count per launch at this batch) against
                 # the issue rate of the chip, 148 SMs x 4 schedulers x 1 instruction/clk at the sampled SM clock
@@ -364,7 +383,10 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": ("step_kernel<reversi> (K7 expand/backup + K5 select + K6 gather)" if K == 1 else
+            "roofline": {"kernel": ("search_fused_kernel (one launch per move: K5 select + K6 gather + K7 expand/backup of all "
+                                    f"{S // K} iterations, {K} leaves per tree, and the policy/value MLP on tcgen05 CTA pairs)"
+                                    if one_launch else
+                                    "step_kernel<reversi> (K7 expand/backup + K5 select + K6 gather)" if K == 1 else
                                     f"step_wave_kernel<reversi, {32 // K} lanes per descent> (K7 + K5 + K6, {K} leaves per tree)"),
                          "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -374,7 +396,7 @@ def run_b200(args):
                          "kernel_ms": step_kernel_ms, "kernel_ms_probe": probe_kind,
                          "net_kernel_ms": net_kernel_ms,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
-                         "sims_per_launch": B * K, "issue": issue},
+                         "sims_per_launch": sims_per_launch, "issue": issue, "static_note": static_note},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
             "selfplay": sp.stats(),
         }
@@ -406,6 +428,9 @@ def run_b200(args):
                 ex["depth_sweep"] = depth_sweep(torch, mcts, selfplay, netmod, args)
                 ex["config3_1024_trees_100_sims"] = config3(torch, mcts, selfplay, net, args)
                 ex["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
+                if one_launch:  # the same search through the per-iteration kernels (select / MLP / step, CUDA graph + PDL)
+                    ex["per_iteration_kernels"] = alt_backend(torch, mcts, selfplay, net, args, same_backend=True,
+                                                              one_launch=False, split=True)
                 if K != 1:  # the strictly sequential search (one leaf per tree and iteration) on the same workload
                     ex["one_leaf_per_iteration"] = alt_backend(torch, mcts, selfplay, net, args, leaves=1, same_backend=True)
             if args.scale_games and args.scale_games != B:
@@ -504,7 +529,22 @@ def probe_iteration_split(torch, sp, n_iter):
 
 
 
-def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=False):
+def probe_one_launch(torch, sp, n_iter, plies=8):
+    """Mean duration of search_fused_kernel (one launch = the whole search of a ply) over `plies` searches of the current
+    positions, CUDA events on the launching stream right around the launch."""
+    evs = []
+    for _ in range(plies):
+        sp.mcts.reset(sp.me, sp.opp)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sp.mcts.search_one_launch(n_iter)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
+
+def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=False, one_launch=None, split=False):
     """The headline workload with the OTHER net backend (library GEMMs if the headline used the tcgen05 MLP
     kernel, and vice versa), or with another number of leaves per iteration, so one bench line shows both."""
     from betazero_b200 import _lib as bzlib
@@ -514,7 +554,7 @@ def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=Fals
     try:
         ev = mcts.FusedNetEvaluator(net, use_kernel=None if use_kernel else False)
         sp = selfplay.BatchedSelfPlay(args.games, args.sims, ev, temp_plies=8, seed=1234, graph_unroll=args.graph_unroll,
-                                      n_leaves=leaves)
+                                      n_leaves=leaves, one_launch=one_launch)
         sp.prepare()
         for _ in range(3):
             sp.play_move()
@@ -528,9 +568,13 @@ def alt_backend(torch, mcts, selfplay, net, args, leaves=None, same_backend=Fals
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         sp.mcts.check_errors()
-        return {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms, "leaves_per_iteration": leaves,
-                "search": search_label(leaves),
-                "net_backend": kernel_net_label(args.games * leaves) if use_kernel else "PyTorch/cuBLASLt GEMMs"}
+        out = {"sims_per_sec": args.games * args.sims / (ms * 1e-3), "ms_per_step": ms, "leaves_per_iteration": leaves,
+               "search": search_label(leaves), "one_launch": bool(sp.mcts.one_launch),
+               "net_backend": kernel_net_label(args.games * leaves) if use_kernel else "PyTorch/cuBLASLt GEMMs"}
+        if split:
+            tree_ms, net_ms, probe = probe_iteration_split(torch, sp, args.sims // leaves - 1)
+            out["per_iteration"] = {"tree_kernel_ms": tree_ms, "net_kernel_ms": net_ms, "probe": probe}
+        return out
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
     finally:

@@ -69,6 +69,24 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
     __trap();
 }
 
+// Short waits beside working warps: poll, but yield the issue slot for BZ_NAP_NS between polls
+#ifndef BZ_NAP_NS
+#define BZ_NAP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_nap(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (BZ_NAP_NS > 0) __nanosleep(BZ_NAP_NS);
+    }
+    __trap();
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
