@@ -68,6 +68,26 @@ inline cudaError_t allow_dynamic_smem(K kernel, int bytes, bool (&done)[64]) {
     return cudaSuccess;
 }
 
+// Debug build (-DBZ_BOUNDS_CHECK, profiles/sanitize.sh): every index the tree / self-play kernels form into a pool is
+// checked against the pool's size before it is used; the first violation is recorded (code, block, thread) and counted,
+// and bz_debug_checks() reports it.  compute-sanitizer is not available on the GPU pool this was developed on; these are
+// the "bounds checks and asserts of your own".  Release builds compile the checks away.
+#ifdef BZ_BOUNDS_CHECK
+static __device__ int g_bz_check[4];  // [0] first failing check's code, [1] block, [2] thread, [3] number of violations (per .cu file)
+#define BZ_CHECK(cond, code)                                              \
+    do {                                                                  \
+        if (!(cond)) {                                                    \
+            if (atomicCAS(&g_bz_check[0], 0, (code)) == 0) {              \
+                g_bz_check[1] = (int)blockIdx.x;                          \
+                g_bz_check[2] = (int)threadIdx.x;                         \
+            }                                                             \
+            atomicAdd(&g_bz_check[3], 1);                                 \
+        }                                                                 \
+    } while (0)
+#else
+#define BZ_CHECK(cond, code) do { } while (0)
+#endif
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // streaming (read-once / write-once) 128-bit global accesses that do not allocate in L1

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(kThreads)
 
     // --- record (board, pi, player, action) in the slot's history -----------------------------
     const int64_t h = (int64_t)s * S.max_plies + ply;
+    BZ_CHECK(s >= 0 && s < S.n_games && ply >= 0 && ply < S.max_plies && action <= 64u, 21);  // history row, move
     float *pi = S.hist_pi + h * A;
     for (int a = lane; a < A; a += 32) pi[a] = 0.f;
     __syncwarp();
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kThreads)
     __syncwarp();  // the record written above is visible to the copying lanes
     const int64_t h0 = (int64_t)s * S.max_plies;
     if (rb != ~0ull) {
+        BZ_CHECK(rb + (unsigned long long)nrec <= (unsigned long long)S.replay_cap && nrec <= S.max_plies, 22);  // replay rows
         for (int r = lane; r < nrec; r += 32) {
             S.rp_me[rb + r] = S.hist_me[h0 + r];
             S.rp_opp[rb + r] = S.hist_opp[h0 + r];
@@ -292,3 +294,13 @@ int bz_philox_u32(uint64_t seed, const int64_t *game_id, const int32_t *ply, uin
 }
 
 }  // extern "C"
+
+#ifdef BZ_BOUNDS_CHECK
+// debug builds: [code of the first failed check, block, thread, violations] of the self-play kernels; clears the record
+extern "C" int bz_debug_checks_selfplay(int *host_out) {
+    int rc = bz::cuda_rc(cudaMemcpyFromSymbol(host_out, bz::g_bz_check, sizeof(int) * 4));
+    if (rc) return rc;
+    const int zero[4] = {0, 0, 0, 0};
+    return bz::cuda_rc(cudaMemcpyToSymbol(bz::g_bz_check, zero, sizeof(zero)));
+}
+#endif

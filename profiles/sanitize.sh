@@ -14,3 +14,9 @@ for tool in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   rc=$?
   echo "== $tool: rc=$rc  $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$log" | tail -1)  [$(grep -c ' ok' "$log") stages ok]"
 done
+# Bounds-check build: the device-side index checks of -DBZ_BOUNDS_CHECK (common.cuh BZ_CHECK), for pools where
+# compute-sanitizer is closed.  Build the variant where nvcc is (profiles/build_variant.sh bounds -DBZ_BOUNDS_CHECK).
+if [ -f build/exp/lib_bounds.so ]; then
+  BETAZERO_B200_LIB=$PWD/build/exp/lib_bounds.so python profiles/sanitize_target.py all > "$OUT/sanitize_bounds.log" 2>&1
+  echo "== bounds-check build: rc=$?"; grep -E "ok|violations" "$OUT/sanitize_bounds.log"
+fi

@@ -1,5 +1,7 @@
-"""Smoke-sized runs of every kernel family for compute-sanitizer (profiles/sanitize.sh).  Each stage checks its own result
-against the oracle / the other implementation, so a sanitizer-clean run is also a correct run."""
+"""Smoke-sized runs of every kernel family for compute-sanitizer, or -- where the sanitizer is not available -- for a
+library built with -DBZ_BOUNDS_CHECK (profiles/sanitize.sh): every pool index the tree / self-play kernels form is checked
+on the device and the violation record is read back at the end.  Each stage also checks its own result against the oracle
+/ the other implementation, so a clean run is also a correct run."""
 import os
 import sys
 
@@ -35,6 +37,18 @@ if stage in ("all", "selfplay"):
     assert st["games"] >= 30 and st["dropped"] == 0, st
     print("selfplay_advance + wave kernels + mlp_pair (PDL) ok", st)
 
+if stage in ("all", "one_launch"):
+    model = net.make_net("mlp", seed=6)
+    for B, sims in ((57, 48), (300, 32)):
+        me_h, opp_h = po.playout_boards(B, seed=B)
+        me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
+        res = []
+        for one in (True, False):
+            s = mcts.BatchedMCTS(mcts.TreePools(B, sims, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False, one_launch=one)
+            res.append([x.clone() for x in s.search(me, opp, sims)])
+        assert all(torch.equal(a, b) for a, b in zip(*res)), B
+    print("search_fused_kernel ok")
+
 if stage in ("all", "mlp"):
     model = net.make_net("mlp", seed=3)
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -56,3 +70,16 @@ if stage in ("all", "env"):
     env.terminal(me, opp)
     env.planes(me, opp)
     print("env kernels ok")
+
+# -DBZ_BOUNDS_CHECK builds export their violation records
+import ctypes  # noqa: E402
+from betazero_b200 import _lib  # noqa: E402
+
+L = _lib.load()
+for name in ("bz_debug_checks_mcts", "bz_debug_checks_selfplay"):
+    if hasattr(L, name):
+        torch.cuda.synchronize()
+        rec = (ctypes.c_int * 4)()
+        assert getattr(L, name)(rec) == 0
+        print(f"{name}: first failed check {rec[0]} (block {rec[1]}, thread {rec[2]}), violations {rec[3]}")
+        assert rec[3] == 0, list(rec)
