@@ -68,6 +68,21 @@ def test_one_launch_headline_config_4096_trees_800_sims():
     assert int(a.root_edges()[0][0].sum()) == 796  # K = 4: the first iteration's four descents all end on the root
 
 
+def test_one_launch_deep_trees_paths_longer_than_a_lane_group():
+    """Peaked priors (policy head x 256) send the descents deep: path entries beyond depth 8 leave the lanes' registers
+    and go through the path array in memory, in the one-launch search as in the per-iteration kernels."""
+    from betazero_b200 import net
+
+    model = net.make_net("mlp", seed=5)
+    with torch.no_grad():
+        model.policy.weight.mul_(256)
+        model.policy.bias.mul_(256)
+    me, opp = _roots(512, 0, start=True)
+    a, b = _search(model, me, opp, 400, True), _search(model, me, opp, 400, False)
+    _same_trees(a, b)
+    assert a.stats()["mean_depth"] > 9.0
+
+
 def test_one_launch_small_boards_and_single_iteration():
     from betazero_b200 import env, mcts, net
 
