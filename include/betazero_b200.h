@@ -233,8 +233,8 @@ int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *
  * A operand) the other island's warps walk their trees.
  * Shape: Reversi, n_leaves == 4 in wave mode (group_lanes 0 or 32), prior_mode BZ_PRIOR_LOGITS_BF16 with
  * eval_stride == 72, n_trees <= 148 * 28 = 4144 (BZ_ERR_ARG otherwise: use the per-iteration entry points).
- * eval_out: [4 * n_trees, 72] bf16 scratch (the net's rows of the last iteration on return); leaf_planes is not
- * written.  n_iterations = simulations per tree / 4. */
+ * eval_out: ignored (may be NULL; earlier versions used it as scratch -- the net's rows now stay in shared memory);
+ * leaf_planes is not written.  n_iterations = simulations per tree / 4. */
 int bz_mcts_search_fused(const bz_tree_pools *pools, const void *weight_image_pair, void *eval_out, int n_iterations,
                          bz_stream_t stream);
 
