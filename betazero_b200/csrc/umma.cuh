@@ -211,6 +211,18 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float2 v) {
     return d;
 }
 
+// the same MMA with the descriptors as 32-bit halves: the low words (the only ones that change from MMA to MMA) stay
+// 32-bit values the compiler can keep and advance in uniform registers
+__device__ __forceinline__ void umma_bf16_pair_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ uint4 bias_pack8(const uint32_t *acc, const float *bias) {
     const float4 b0 = *reinterpret_cast<const float4 *>(bias), b1 = *reinterpret_cast<const float4 *>(bias + 4);
     const float2 s0 = add2(acc[0], acc[1], b0.x, b0.y), s1 = add2(acc[2], acc[3], b0.z, b0.w);
