@@ -137,7 +137,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_pai
     const int q = warp & 3, g = warp >> 2;
     const int r = (q & 1) * 32 + lane;                                // accumulator row of this thread
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);          // TMEM lanes of this warp
-    constexpr uint64_t kDescHi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    constexpr uint32_t kDescLo = 1u << 16, kDescHi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // umma_desc, as 32-bit halves
     uint32_t woff = 0;
 
 #pragma unroll 1
@@ -167,17 +167,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_pai
             const uint32_t idesc = umma_idesc(kPairRows, N);
             const uint32_t elected = elect_one();
             const uint32_t nk = (uint32_t)K / 16;
+            // ONE elected-thread region for the layer, descriptors as 32-bit halves: the compiler keeps and advances them
+            // in uniform registers (an `if (elected)` around every MMA costs ~7 R2UR moves per instruction)
+            if (elected) {
+                const uint32_t tmem_u = tmem;
 #pragma unroll 4
-            for (uint32_t k = 0; k < nk; ++k) {
-                const uint32_t off = k >> 2, kk = (k & 3) * 32u;
-                const uint64_t adesc = kDescHi | (uint64_t)(((sA + off * kSlabA + kk) >> 4) & 0x3FFFu);
-                const uint64_t bdesc = kDescHi | (uint64_t)(((sW + woff + off * slabW + kk) >> 4) & 0x3FFFu);
-                if (elected) umma_bf16_pair(tmem, adesc, bdesc, idesc, k > 0);
-            }
-            if (elected)
+                for (uint32_t k = 0; k < nk; ++k) {
+                    const uint32_t off = k >> 2, kk = (k & 3) * 32u;
+                    const uint32_t alo = kDescLo | (((sA + off * kSlabA + kk) >> 4) & 0x3FFFu);
+                    const uint32_t blo = kDescLo | (((sW + woff + off * slabW + kk) >> 4) & 0x3FFFu);
+                    umma_bf16_pair_lohi(tmem_u, alo, blo, kDescHi32, idesc, k > 0);
+                }
                 asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mma_bar),
                              "h"((uint16_t)3)
                              : "memory");
+            }
             __syncwarp();
             PAIR_TRACE(6 + 5 * layer);
         }

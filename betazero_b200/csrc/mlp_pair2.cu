@@ -136,7 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_pai
 
     if (control) {
         // ================= control warp (converged; one elected lane per tcgen05 instruction) =================
-        constexpr uint64_t kDescHi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        constexpr uint32_t kDescLo = 1u << 16, kDescHi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // umma_desc, as 32-bit halves
         const uint32_t elected = elect_one();
 #pragma unroll 1
         for (int layer = 0; layer < 4; ++layer) {
@@ -160,18 +160,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_pai
                     P2_TRACE(2 + 8 * layer + 4 * t);
                     const uint32_t nk = (uint32_t)K / 16;
                     const uint32_t sAt = sA + (uint32_t)t * kSmemA, dcol = tmem + (uint32_t)t * 128u;
+                    // ONE elected-thread region per tile and layer, descriptors as 32-bit halves (uniform registers)
+                    if (elected) {
 #pragma unroll 4
-                    for (uint32_t k = 0; k < nk; ++k) {
-                        const uint32_t off = k >> 2, kk = (k & 3) * 32u;
-                        const uint64_t adesc = kDescHi | (uint64_t)(((sAt + off * kSlabA + kk) >> 4) & 0x3FFFu);
-                        const uint64_t bdesc = kDescHi | (uint64_t)(((sWl + off * slabW + kk) >> 4) & 0x3FFFu);
-                        if (elected) umma_bf16_pair(dcol, adesc, bdesc, idesc, k > 0);
-                    }
-                    if (elected)
+                        for (uint32_t k = 0; k < nk; ++k) {
+                            const uint32_t off = k >> 2, kk = (k & 3) * 32u;
+                            const uint32_t alo = kDescLo | (((sAt + off * kSlabA + kk) >> 4) & 0x3FFFu);
+                            const uint32_t blo = kDescLo | (((sWl + off * slabW + kk) >> 4) & 0x3FFFu);
+                            umma_bf16_pair_lohi(dcol, alo, blo, kDescHi32, idesc, k > 0);
+                        }
                         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                                          mma_bar(t)),
                                      "h"((uint16_t)3)
                                      : "memory");
+                    }
                     __syncwarp();
                     P2_TRACE(3 + 8 * layer + 4 * t);
                 }
