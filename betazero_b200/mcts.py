@@ -225,7 +225,8 @@ class BatchedMCTS:
                  one_launch: bool | None = None):
         self.pools, self.evaluator = pools, evaluator
         # one_launch: run the whole search of a move in ONE kernel (bz_mcts_search_fused) when the shape allows --
-        # Reversi, 4 leaves per iteration in wave mode, the bf16 MLP through its tcgen05 kernel path, at most 4144 trees.
+        # Reversi, 4 leaves per iteration in wave mode, the bf16 MLP through its tcgen05 kernel path (more than 4144 trees
+        # are searched in chunks, one launch each).
         # None = whenever possible; False = always the per-iteration kernels; True = raise if the shape does not fit.
         self._one_launch_arg = one_launch
         # root exploration noise (self-play only; 0 = off, which every parity test uses)
@@ -258,7 +259,7 @@ class BatchedMCTS:
         return (isinstance(ev, FusedNetEvaluator) and ev.use_kernel is not False and getattr(ev, "own_launches", 0) == 1
                 and getattr(net, "_image_pair", None) is not None and self.fused
                 and p.game == GAME_REVERSI and p.n_leaves == 4 and p.group_lanes in (0, 32)
-                and p.prior_mode == PRIOR_LOGITS_BF16 and p.eval_stride == 72 and 0 < p.n_trees <= self.ONE_LAUNCH_MAX_TREES)
+                and p.prior_mode == PRIOR_LOGITS_BF16 and p.eval_stride == 72 and p.n_trees > 0)
 
     @property
     def one_launch(self) -> bool:
@@ -267,7 +268,7 @@ class BatchedMCTS:
         ok = self.one_launch_ok()
         if self._one_launch_arg and not ok:
             raise RuntimeError("one_launch=True, but bz_mcts_search_fused does not cover this search (it needs Reversi, "
-                               "n_leaves = 4 in wave mode, the bf16 MLP kernel path and at most 4144 trees)")
+                               "n_leaves = 4 in wave mode and the bf16 MLP kernel path)")
         return ok
 
     def search_one_launch(self, n_iterations: int) -> None:
@@ -275,7 +276,7 @@ class BatchedMCTS:
         _lib.check(self._L.bz_mcts_search_fused(self.pools._ref, _lib.dptr(self.evaluator.net._image_pair),
                                                 _lib.dptr(self.prior_w), int(n_iterations), _lib.stream_ptr()),
                    "bz_mcts_search_fused")
-        self.launches += 1
+        self.launches += -(-self.pools.n_trees // self.ONE_LAUNCH_MAX_TREES)  # one launch per chunk of <= 4144 trees
 
     # -- single kernels ------------------------------------------------------------------------
     def reset(self, root_me: torch.Tensor, root_opp: torch.Tensor) -> None:

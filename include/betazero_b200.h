@@ -232,7 +232,8 @@ int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *
  * bz_mlp_forward_pair resident in shared memory for the whole search, the leaf planes written from registers into the
  * A operand) the other island's warps walk their trees.
  * Shape: Reversi, n_leaves == 4 in wave mode (group_lanes 0 or 32), prior_mode BZ_PRIOR_LOGITS_BF16 with
- * eval_stride == 72, n_trees <= 148 * 28 = 4144 (BZ_ERR_ARG otherwise: use the per-iteration entry points).
+ * eval_stride == 72 (BZ_ERR_ARG otherwise: use the per-iteration entry points).  One launch holds 148 * 28 = 4144
+ * trees; more trees are searched in equal chunks, one launch after the other on the stream.
  * eval_out: ignored (may be NULL; earlier versions used it as scratch -- the net's rows now stay in shared memory);
  * leaf_planes is not written.  n_iterations = simulations per tree / 4. */
 int bz_mcts_search_fused(const bz_tree_pools *pools, const void *weight_image_pair, void *eval_out, int n_iterations,

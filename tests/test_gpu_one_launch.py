@@ -48,7 +48,7 @@ def _same_trees(a, b):
     assert torch.equal(arena_a[live], arena_b[live])  # every node block of every tree
 
 
-@pytest.mark.parametrize("B", [1, 13, 28, 29, 56, 57, 300, 4144])
+@pytest.mark.parametrize("B", [1, 13, 28, 29, 56, 57, 300, 4144, 4145, 9000])  # above 4144: chunks, one launch each
 def test_one_launch_search_builds_the_same_trees(B):
     from betazero_b200 import net
 
@@ -68,7 +68,8 @@ def test_one_launch_headline_config_4096_trees_800_sims():
     assert int(a.root_edges()[0][0].sum()) == 796  # K = 4: the first iteration's four descents all end on the root
 
 
-def test_one_launch_deep_trees_paths_longer_than_a_lane_group():
+@pytest.mark.parametrize("B,n_sims", [(512, 400), (4300, 240)])  # 4300 trees: two chunks, each with its own part of the path array
+def test_one_launch_deep_trees_paths_longer_than_a_lane_group(B, n_sims):
     """Peaked priors (policy head x 256) send the descents deep: path entries beyond depth 8 leave the lanes' registers
     and go through the path array in memory, in the one-launch search as in the per-iteration kernels."""
     from betazero_b200 import net
@@ -77,8 +78,8 @@ def test_one_launch_deep_trees_paths_longer_than_a_lane_group():
     with torch.no_grad():
         model.policy.weight.mul_(256)
         model.policy.bias.mul_(256)
-    me, opp = _roots(512, 0, start=True)
-    a, b = _search(model, me, opp, 400, True), _search(model, me, opp, 400, False)
+    me, opp = _roots(B, 0, start=True)
+    a, b = _search(model, me, opp, n_sims, True), _search(model, me, opp, n_sims, False)
     _same_trees(a, b)
     assert a.stats()["mean_depth"] > 9.0
 
@@ -131,7 +132,7 @@ def test_one_launch_is_refused_outside_its_shape():
 
     model = net.make_net("mlp", seed=1)
     big = mcts.BatchedMCTS(mcts.TreePools(4145, 8, n_leaves=4, arena_units=64), mcts.FusedNetEvaluator(model), use_graph=False)
-    assert not big.one_launch  # falls back to the per-iteration kernels
+    assert big.one_launch  # more than one launch's 4144 trees: searched in chunks
     for kw in (dict(n_leaves=2), dict(n_leaves=1), dict(n_leaves=4, group_lanes=8)):
         s = mcts.BatchedMCTS(mcts.TreePools(64, 8, **kw), mcts.FusedNetEvaluator(model), use_graph=False)
         assert not s.one_launch
