@@ -425,6 +425,7 @@ def run_b200(args):
                 ex["env_cpu_baseline"] = env_cpu_baseline(ex)
             if hasattr(net, "forward_raw"):
                 ex["full_game"] = full_game(torch, mcts, selfplay, net, args)
+                ex["tree_reuse"] = tree_reuse(torch, mcts, selfplay, net, args)
                 ex["depth_sweep"] = depth_sweep(torch, mcts, selfplay, netmod, args)
                 ex["config3_1024_trees_100_sims"] = config3(torch, mcts, selfplay, net, args)
                 ex["other_net_backend"] = alt_backend(torch, mcts, selfplay, net, args)
@@ -617,6 +618,52 @@ def at_scale(torch, mcts, selfplay, net, args, games, leaves):
                 "launches_per_move": (2 + -(-G // sp.mcts.ONE_LAUNCH_MAX_TREES)) if sp.mcts.one_launch else None}
     except Exception as e:  # never let the side measurement break the headline line
         return {"games_per_gpu": G, "leaves_per_iteration": leaves, "error": f"{type(e).__name__}: {e}"}
+    finally:
+        from betazero_b200 import _lib as bzlib
+
+        bzlib.set_pdl(False)
+
+
+def tree_reuse(torch, mcts, selfplay, net, args, plies=40):
+    """Opt-in tree reuse (bz_mcts_reroot): every move's search continues on the subtree of the move played, so a move's
+    root carries the kept visits plus sims/move new ones and the trees go deeper.  Reported: the same sims/s metric (new
+    simulations only), the re-rooting kernel's share of a ply, the root visit totals and the tree depth."""
+    B, S, K = args.games, args.sims, args.leaves
+    try:
+        ev = mcts.FusedNetEvaluator(net, use_kernel=None if getattr(args, "kernel_net", False) else False)
+        sp = selfplay.BatchedSelfPlay(B, S, ev, temp_plies=8, seed=4321, graph_unroll=args.graph_unroll, n_leaves=K, reuse=True)
+        sp.prepare()
+        for _ in range(4):
+            sp.play_move()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(plies):
+            sp.play_move()
+        e1.record()
+        torch.cuda.synchronize()
+        sp.mcts.check_errors()
+        ms = e0.elapsed_time(e1) / plies
+        st = sp.mcts.stats()
+        inherited = float(sp.pools.inherited.float().mean().item())
+        root_visits = float(sp.pools.sim_count.float().mean().item())
+        units = float(sp.pools.arena_used.float().mean().item())
+        # the re-rooting kernel alone, on the trees as they stand (same move twice is not possible: time one call)
+        sp.search()
+        sp.advance()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        sp.mcts.advance(sp.last_action, sp.me, sp.opp)
+        r1.record()
+        torch.cuda.synchronize()
+        return {"plies": plies, "games_per_gpu": B, "leaves_per_iteration": K, "ms_per_ply": ms,
+                "sims_per_sec": B * S / (ms * 1e-3), "reroot_kernel_ms": r0.elapsed_time(r1),
+                "mean_root_visits_after_search": root_visits, "mean_inherited_visits": inherited,
+                "mean_depth": st["mean_depth"], "mean_arena_units_used": units, "arena_units": sp.pools.arena_units,
+                "pool_bytes": sp.pools.nbytes() + sp.pools.scratch.numel() * 4,
+                "note": "sims/s counts the NEW simulations of a move only; off by default (the goldens pin a fresh tree per move)"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
     finally:
         from betazero_b200 import _lib as bzlib
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "bz_mcts_root_edges": [_PP, ptr, ptr, ptr, ptr],
     "bz_mcts_best_action": [_PP, ptr, ptr],
     "bz_mcts_root_noise": [_PP, ptr, _F, ptr],
+    "bz_mcts_reroot": [_PP, ptr, ptr, ptr, ptr, _INT, ptr, ptr],
     "bz_hash_eval": [ptr, ptr, _U64, _INT, ptr, ptr, _I64, ptr],
     "bz_selfplay_init": [_SP, _I64, ptr],
     "bz_selfplay_advance": [_SP, _PP, ptr, ptr],
@@ -93,7 +94,7 @@ def lib_path() -> str:
     return _build.LIB
 
 
-ABI_VERSION = 4  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
+ABI_VERSION = 5  # BZ_ABI_VERSION of include/betazero_b200.h this module's structs and signatures mirror
 
 
 def load():

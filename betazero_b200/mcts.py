@@ -39,19 +39,25 @@ class TreePools:
     def __init__(self, n_trees: int, sims_cap: int, game: int = GAME_REVERSI, board_size: int = 8,
                  c_puct: float = 1.25, arena_units: int | None = None, max_depth: int | None = None,
                  prior_mode: int = PRIOR_WEIGHTS, eval_stride: int = 0, group_lanes: int = 0, n_leaves: int = 1,
-                 device="cuda"):
+                 device="cuda", reuse: bool = False):
         if game not in (GAME_REVERSI, GAME_TTT):
             raise ValueError("game must be GAME_REVERSI or GAME_TTT")
         self.game, self.board_size = game, (3 if game == GAME_TTT else board_size)
         self.n_trees, self.sims_cap = int(n_trees), int(sims_cap)
         self.n_actions = 9 if game == GAME_TTT else 65
         self.c_puct = float(c_puct)
+        # reuse: the trees may be kept across moves (BatchedMCTS.advance / bz_mcts_reroot).  The arena then holds the
+        # kept subtree AND the worst case of the next search: twice the default size, and a subtree is only kept if it
+        # leaves room for sims_cap worst-case nodes (reuse_cap_units), so a search still cannot overflow the arena.
+        self.reuse = bool(reuse)
+        worst = max(self.sims_cap, 1) * _NODE_UNITS[game]
         if arena_units is None:
-            arena_units = min(max(self.sims_cap, 1) * _NODE_UNITS[game], MAX_ARENA_UNITS)
+            arena_units = min(worst * (2 if self.reuse else 1), MAX_ARENA_UNITS)
         arena_units = max(int(arena_units), 18)
         if arena_units > MAX_ARENA_UNITS:
             raise ValueError(f"arena_units {arena_units} exceeds {MAX_ARENA_UNITS}")
         self.arena_units = arena_units
+        self.reuse_cap_units = max(arena_units - worst, 0)
         self.max_depth = int(max_depth or (16 if game == GAME_TTT else 128))
         self.prior_mode, self.eval_stride = int(prior_mode), int(eval_stride)
         self.device = torch.device(device)
@@ -75,6 +81,9 @@ class TreePools:
         self.edge_count, self.sim_count = torch.zeros(B, dtype=torch.int32, device=dev), e(B, torch.int32)
         self.depth_sum, self.error = e(B, torch.int32), torch.zeros(B, dtype=torch.int32, device=dev)
         self.arena = e(B * self.arena_units * 8, torch.int32)
+        # scratch of bz_mcts_reroot (the subtree is compacted there and copied back) + the visits every root inherited
+        self.scratch = e(B * self.arena_units * 8, torch.int32) if self.reuse else None
+        self.inherited = torch.zeros(B, dtype=torch.int32, device=dev)
         self.path, self.path_len = e(R * self.max_depth * 4, torch.int32), torch.zeros(R, dtype=torch.int32, device=dev)
         self.leaf_parent = e(R, torch.int32)
         self.leaf_me, self.leaf_opp, self.leaf_mask = e(R, torch.int64), e(R, torch.int64), e(R, torch.int64)
@@ -284,6 +293,7 @@ class BatchedMCTS:
         if root_me.numel() != p.n_trees or root_opp.numel() != p.n_trees:
             raise ValueError("one root per tree expected")
         _lib.check(self._L.bz_mcts_reset(p._ref, _lib.dptr(root_me), _lib.dptr(root_opp), _lib.stream_ptr()), "bz_mcts_reset")
+        p.inherited.zero_()
         self.launches += 1
 
     def select(self) -> None:
@@ -440,10 +450,28 @@ class BatchedMCTS:
             raise _lib.BzError(f"tree pool overflow (codes {codes}: 1 = arena, 2 = path depth); "
                                "enlarge arena_units / max_depth")
 
+    def advance(self, action: torch.Tensor, root_me: torch.Tensor, root_opp: torch.Tensor, cap_units: int | None = None) -> None:
+        """Tree reuse (opt-in, ``TreePools(reuse=True)``): the game of tree t has played ``action[t]`` and stands at
+        ``(root_me[t], root_opp[t])``; every tree is re-rooted at the child that move leads to (bz_mcts_reroot) -- or
+        emptied at the new position if that child was never expanded, is another position (a new game) or its subtree
+        is larger than ``cap_units`` (default: what leaves room for a whole worst-case search).  The next ``run(n)``
+        adds n simulations to the kept statistics.  Definition: oracle/mcts_ref.py MCTS.advance."""
+        p = self.pools
+        if p.scratch is None:
+            raise RuntimeError("tree reuse needs TreePools(reuse=True) (a scratch arena and room for the kept subtree)")
+        if action.numel() != p.n_trees or root_me.numel() != p.n_trees or root_opp.numel() != p.n_trees:
+            raise ValueError("one action and one position per tree expected")
+        if action.dtype != torch.uint8:
+            raise TypeError("action: uint8 tensor expected")
+        cap = p.reuse_cap_units if cap_units is None else int(cap_units)
+        _lib.check(self._L.bz_mcts_reroot(p._ref, _lib.dptr(p.scratch), _lib.dptr(action), _lib.dptr(root_me), _lib.dptr(root_opp),
+                                          cap, _lib.dptr(p.inherited), _lib.stream_ptr()), "bz_mcts_reroot")
+        self.launches += 1
+
     def stats(self) -> dict:
         """mean path depth d and mean edges per expanded node b of the last search (roofline model)."""
         p = self.pools
-        sims = int(p.sim_count[: p.n_trees].sum().item())
+        sims = int(p.sim_count[: p.n_trees].sum().item()) - int(p.inherited[: p.n_trees].sum().item())
         depth = int(p.depth_sum[: p.n_trees].sum().item())
         edges = int(p.edge_count[: p.n_trees].sum().item())
         units = int(p.arena_used[: p.n_trees].sum().item())

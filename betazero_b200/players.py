@@ -55,24 +55,58 @@ class MCTSPlayer(ReversiPlayer):
     the deterministic hash pseudo-net is used (parity / tests)."""
 
     def __init__(self, symbol, net=None, n_sims: int = 100, c_puct: float = 1.25, size: int = 8, evaluator=None,
-                 salt: int = 0, n_leaves: int = 1):
+                 salt: int = 0, n_leaves: int = 1, reuse: bool = False):
         self.symbol = symbol  # 1 for X, -1 for O
         self.n_sims, self.size = int(n_sims), int(size)
         # n_leaves > 1: virtual-loss descents per iteration (n_sims must be a multiple); 1 = the sequential search
-        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_REVERSI, board_size=size, c_puct=c_puct, n_leaves=n_leaves)
+        # reuse: keep the subtree of (own move, opponent's reply) from one get_move to the next (oracle/mcts_ref.py
+        # MCTS.advance); every call then adds n_sims simulations to what the previous searches left below the new root
+        self.reuse = bool(reuse)
+        self.pools = mcts.TreePools(1, self.n_sims, game=mcts.GAME_REVERSI, board_size=size, c_puct=c_puct, n_leaves=n_leaves,
+                                    reuse=self.reuse)
         self.search = mcts.BatchedMCTS(self.pools, _make_evaluator(evaluator, net, salt), use_graph=False)
         self.last_counts = None
         self.last_policy = None
+        self.last_inherited = 0   # visits the root of the last search started with (reuse)
+        self._after_own = None    # (me, opp) device tensors + occupancy after this player's last move, opponent to move
+        self._own_action = None
+
+    def _continue_or_reset(self, me_t, opp_t, me: int, opp: int) -> None:
+        """reuse: follow the own move and the opponent's reply (a new disc, or a pass) down the kept tree"""
+        if self._after_own is not None:
+            pm, po_, occ = self._after_own
+            new = (me | opp) & ~occ
+            if new == 0 or (new & (new - 1)) == 0:  # one reply (or a pass); anything else: not the same game, start over
+                b = 64 if new == 0 else new.bit_length() - 1
+                self.search.advance(self._own_action, pm, po_)
+                self.search.advance(torch.tensor([b], dtype=torch.uint8, device=me_t.device), me_t, opp_t)
+                return
+        self.search.reset(me_t, opp_t)
 
     def get_move(self, board):
         if int(board.size) != self.size:
             raise ValueError(f"this player was built for {self.size}x{self.size} boards")
         me, opp = _grid_to_bits(np.asarray(board.board), self.symbol, 8)
-        cnt, pi, _ = self.search.search(env.to_device_u64(np.array([me], np.uint64)),
-                                        env.to_device_u64(np.array([opp], np.uint64)), self.n_sims)
-        a = int(self.search.best_action()[0].item())
+        me_t, opp_t = env.to_device_u64(np.array([me], np.uint64)), env.to_device_u64(np.array([opp], np.uint64))
+        if self.reuse:
+            self._continue_or_reset(me_t, opp_t, me, opp)
+            self.last_inherited = int(self.pools.inherited[0].item())
+            self.search.run(self.n_sims)
+            cnt, pi, _ = self.search.root_policy()
+            self.search.check_errors()
+        else:
+            cnt, pi, _ = self.search.search(me_t, opp_t, self.n_sims)
+        best = self.search.best_action()
+        a = int(best[0].item())
         self.last_counts = cnt[0].cpu().numpy().copy()
         self.last_policy = pi[0].cpu().numpy().copy()
+        if self.reuse:
+            if a <= 64:
+                pm, po_, _ = env.apply(me_t, opp_t, best.clone(), self.size)
+                occ = (me | opp) | ((1 << a) if a < 64 else 0)
+                self._after_own, self._own_action = (pm, po_, occ), best.clone()
+            else:
+                self._after_own = None
         if a >= 64:  # pass (64) or finished game (255): the reference convention for "no moves"
             return None, None
         return a >> 3, a & 7

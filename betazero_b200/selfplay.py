@@ -26,12 +26,16 @@ class BatchedSelfPlay:
                  temp_plies: int = 0, seed: int = 0, replay_cap: int | None = None, rank: int = 0, world: int = 1,
                  arena_units: int | None = None, use_graph: bool = True, graph_unroll: int = 16,
                  dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.25, n_leaves: int = 1, device="cuda",
-                 one_launch: bool | None = None):
+                 one_launch: bool | None = None, reuse: bool = False):
         self.n_games, self.n_sims, self.board_size = int(n_games), int(n_sims), int(board_size)
         self.rank, self.world = int(rank), int(world)
         self.device = torch.device(device)
+        # reuse: a move's search continues on the subtree of the move played (opt-in; bz_mcts_reroot) -- n_sims MORE
+        # simulations per move on top of the kept ones; the default is a fresh tree per move, which the goldens pin
+        self.reuse = bool(reuse)
+        self._moves = 0
         self.pools = TreePools(n_games, n_sims, board_size=board_size, c_puct=c_puct, arena_units=arena_units,
-                               n_leaves=n_leaves, device=device)
+                               n_leaves=n_leaves, device=device, reuse=reuse)
         self.mcts = BatchedMCTS(self.pools, evaluator, use_graph=use_graph, graph_unroll=graph_unroll,
                                 dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps,
                                 noise_seed=seed * 7919 + rank, one_launch=one_launch)
@@ -72,8 +76,12 @@ class BatchedSelfPlay:
         if (self.mcts.use_graph and self.mcts._graph is None and not self.mcts.one_launch
                 and self.n_sims // self.pools.n_leaves - 1 >= self.mcts.unroll):
             self.mcts.prepare()  # lazily, before the roots are set: play_move() works without an explicit prepare()
-        self.mcts.reset(self.me, self.opp)
+        if self.reuse and self._moves > 0:
+            self.mcts.advance(self.last_action, self.me, self.opp)  # slots whose game restarted get an empty tree
+        else:
+            self.mcts.reset(self.me, self.opp)
         self.mcts.run(self.n_sims)
+        self._moves += 1
 
     def advance(self) -> None:
         _lib.check(self._L.bz_selfplay_advance(self._ref, self.pools._ref, _lib.dptr(self.last_action),

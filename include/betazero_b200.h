@@ -32,7 +32,7 @@ extern "C" {
 #define BZ_OK 0
 #define BZ_ERR_ARG (-1)
 #define BZ_ERR_UNALIGNED (-2)
-#define BZ_ABI_VERSION 4
+#define BZ_ABI_VERSION 5
 
 #define BZ_REVERSI_ACTIONS 65
 #define BZ_TTT_ACTIONS 9
@@ -238,6 +238,23 @@ int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *
  * leaf_planes is not written.  n_iterations = simulations per tree / 4. */
 int bz_mcts_search_fused(const bz_tree_pools *pools, const void *weight_image_pair, void *eval_out, int n_iterations,
                          bz_stream_t stream);
+
+/* Tree reuse across moves (opt-in; the default -- bz_mcts_reset before every search -- is what the goldens pin).
+ * After the game of tree t has played action[t] and stands at (new_me[t], new_opp[t]), mover-relative for the side to
+ * move there, the tree is re-rooted at the child that action leads to: the child's subtree -- statistics, priors,
+ * shape -- is compacted to the front of the tree's arena and becomes the tree; sim_count[t] becomes the visit count of
+ * the edge into the new root.  The subtree is kept iff the root has an edge for action[t], the child behind it has
+ * been expanded, the child's board equals the new position (a slot whose game ended and restarted therefore starts an
+ * empty tree) and the subtree occupies at most cap_units arena units; otherwise the tree is emptied at the new
+ * position exactly as bz_mcts_reset would (cap_units * 8 + cap_units / 2 + 1 <= arena_units * 8, BZ_ERR_ARG otherwise:
+ * the top of the scratch arena is the copy's queue).  Choose cap_units <= arena_units - 18 * (simulations of the next search):
+ * then the next search cannot overflow the arena.  The next search (bz_mcts_search_fused, or select / step ...) adds its
+ * simulations to the kept statistics, as AlphaZero's self-play does; Player.get_move (reversi_players.py:5-8) sees
+ * visit counts that include the inherited ones.
+ * scratch_arena: uint32 [n_trees * arena_units * 8], 32-byte aligned (contents are scratch).  inherited (may be NULL):
+ * int32 [n_trees], the visits each new root starts with (0: empty tree).  Definition: oracle/mcts_ref.py MCTS.advance. */
+int bz_mcts_reroot(const bz_tree_pools *pools, void *scratch_arena, const uint8_t *action, const uint64_t *new_me,
+                   const uint64_t *new_opp, int cap_units, int32_t *inherited, bz_stream_t stream);
 
 /* Root exploration noise (AlphaZero self-play; OFF in every parity test): for each tree whose
  * root is expanded, P[e] <- (1 - eps) * P[e] + eps * noise[a_e] / sum over the root's edges of

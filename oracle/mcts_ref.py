@@ -36,6 +36,12 @@ Frozen semantics
 * Backup: ``v`` is the value for the side to move at the leaf; walking up, ``v = -v`` before
   each edge update (the sign flips every ply, pass plies included); ``N += 1; W = W + v``.
 * Dirichlet noise off, one leaf per tree per iteration (no virtual loss).
+* Tree reuse across moves is OPT-IN (``MCTS.advance``; every golden uses a fresh tree per move): after a move the
+  search may continue on the subtree of the child the move leads to.  That subtree is kept iff the child has been
+  expanded and the subtree's size, counted in the engine's arena units (``node_units``), is at most ``cap_units``;
+  otherwise the next search starts on an empty tree.  A kept root keeps its statistics, and the next search ADDS its
+  simulations to them (the root's visit total under the square root continues from the visits of the edge that led
+  to it).
 """
 from __future__ import annotations
 
@@ -225,6 +231,27 @@ class MCTS:
         self.n_sims += 1
         self._leaf = None
 
+    # -- tree reuse across moves (opt-in) -------------------------------------------------------
+    def advance(self, action: int, board, player, cap_units: int | None = None) -> bool:
+        """The game has played ``action`` from the root position and stands at ``(board, player)``.  Keep the subtree
+        of the child that action leads to -- iff that child has been expanded and the subtree occupies at most
+        ``cap_units`` arena units (None: no limit) -- as the tree of the next search; otherwise start an empty tree
+        at the new position.  Returns True if the subtree was kept.
+
+        The kept root's ``visits`` (virtual-loss mode: descents that have entered it) equal the N of the edge that led
+        to it, and ``1 + sum(child N)`` of the one-leaf mode is the same number: the next search continues from it."""
+        r = self.root
+        child = None
+        if r is not None and r.actions is not None and action in r.actions:
+            child = r.children[r.actions.index(action)]
+        if child is not None and child.value is None and child.actions is not None and (
+                cap_units is None or subtree_units(child) <= cap_units):
+            self.root = child
+            self._leaf = None
+            return True
+        self.reset(board, player)
+        return False
+
     def run(self, n_sims: int):
         for _ in range(n_sims):
             status, me, opp = self.select()
@@ -326,6 +353,25 @@ class MCTS:
         return cnt, W, P
 
 
+def node_units(n_edges: int) -> int:
+    """Arena units (32 bytes) of an expanded node with ``n_edges`` edges in the engine's tree layout: an 8-word header
+    and four words per edge, rounded up to whole units (include/betazero_b200.h)."""
+    return (8 + 4 * n_edges + 7) >> 3
+
+
+def subtree_units(node) -> int:
+    """Arena units of the expanded nodes of the subtree below (and including) ``node``; unexpanded and terminal
+    children occupy nothing."""
+    total, stack = 0, [node]
+    while stack:
+        nd = stack.pop()
+        if nd is None or nd.actions is None:
+            continue
+        total += node_units(len(nd.actions))
+        stack.extend(nd.children)
+    return total
+
+
 def policy_from_counts(counts):
     """pi = N / sum(N) in float32 (zeros if nothing was visited)."""
     counts = np.asarray(counts, dtype=np.int32)
@@ -340,16 +386,20 @@ def pick_move(counts) -> int:
     return int(np.argmax(np.asarray(counts)))  # np.argmax returns the first maximum
 
 
-def self_play_game(game, n_sims: int, c_puct: float, evaluator, max_plies: int = 200, leaves: int = 1):
+def self_play_game(game, n_sims: int, c_puct: float, evaluator, max_plies: int = 200, leaves: int = 1, reuse: bool = False,
+                   cap_units: int | None = None):
     """One deterministic self-play game in the order of the reference episode loops
     (reversi_terminal.py:16-38 / tic_tac_toe.py:13-34): search, move (or pass), terminal test,
     flip player.  Returns a list of (me, opp, player, counts, action) per ply and the winner.
-    ``leaves`` > 1: every search makes that many virtual-loss descents per iteration (MCTS.run_vl)."""
+    ``leaves`` > 1: every search makes that many virtual-loss descents per iteration (MCTS.run_vl).
+    ``reuse``: the tree of a move continues on the subtree of the move played (MCTS.advance) instead of starting empty."""
     board, player = game.initial()
     history = []
+    m = None
     while game.terminal_value(board, player) is None and len(history) < max_plies:
-        m = MCTS(game, c_puct, evaluator)
-        m.reset(board, player)
+        if m is None or not reuse:
+            m = MCTS(game, c_puct, evaluator)
+            m.reset(board, player)
         if leaves > 1:
             m.run_vl(n_sims, leaves)
         else:
@@ -359,6 +409,8 @@ def self_play_game(game, n_sims: int, c_puct: float, evaluator, max_plies: int =
         me, opp = game.wire(board, player)
         history.append((me, opp, player, cnt, a))
         board, player = game.next(board, player, a)
+        if reuse:
+            m.advance(a, board, player, cap_units)
     tv = game.terminal_value(board, player)
     winner = 0 if tv is None else int(tv) * player
     return history, winner

@@ -126,6 +126,10 @@ def _declare(L):
     L.orc_mcts_expand_backup_vl.argtypes = [C.c_void_p, C.c_int, _pf, C.c_float]
     L.orc_mcts_search_hash_vl.argtypes = [C.c_int, C.c_int, C.c_float, C.c_uint64, _pu64, _pu64, C.c_int64, C.c_int, C.c_int,
                                           _pi32, _pf, _pf, _pi64]
+    L.orc_mcts_advance.argtypes = [C.c_void_p, C.c_int, _p8, C.c_int, C.c_int64]
+    L.orc_mcts_advance.restype = C.c_int
+    L.orc_mcts_play_hash.argtypes = [C.c_int, C.c_int, C.c_float, C.c_uint64, _pu64, _pu64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int64, _pi32, _pu8, _pu8]
     L.orc_mcts_batch_select_vl.argtypes = [_pp, C.c_int64, C.c_int, _pu64, _pu64, _pu8, _pf]
     L.orc_mcts_batch_expand_backup_vl.argtypes = [_pp, C.c_int64, C.c_int, _pf, _pf, C.c_int]
 
@@ -413,6 +417,24 @@ def search_hash(me, opp, n_sims, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0,
         lib().orc_mcts_search_hash(game, size, c_puct, salt, _ptr(me, _pu64), _ptr(opp, _pu64), n, n_sims,
                                    _ptr(cnt, _pi32), _ptr(W, _pf), _ptr(P, _pf), _ptr(c, _pi64))
     return cnt, W, P, dict(nodes=int(c[0]), edges=int(c[1]), sum_depth=int(c[2]), sims=int(c[3]))
+
+
+def play_hash(me, opp, n_sims, plies, game=GAME_REVERSI, size=8, c_puct=1.25, salt=0, leaves=1, reuse=False, cap_units=-1):
+    """``plies`` moves of deterministic play from every (me, opp) root with the hash evaluator (orc_mcts_play_hash): a
+    search of n_sims simulations per move, the most visited action is played, and -- ``reuse`` -- the next move's tree
+    is the kept subtree of the move played (MCTS.advance, at most ``cap_units`` arena units; -1 = no limit).
+    Returns (counts int32[n, plies, A], actions uint8[n, plies] (255 after the game's end), kept uint8[n, plies])."""
+    me, opp = _c(me, np.uint64), _c(opp, np.uint64)
+    A = 9 if game == GAME_TTT else 65
+    n = me.size
+    if n_sims % leaves:
+        raise ValueError("n_sims must be a multiple of leaves")
+    cnt = np.zeros((n, plies, A), np.int32)
+    act = np.zeros((n, plies), np.uint8)
+    kept = np.zeros((n, plies), np.uint8)
+    lib().orc_mcts_play_hash(game, size, c_puct, salt, _ptr(me, _pu64), _ptr(opp, _pu64), n, n_sims, leaves, plies,
+                             1 if reuse else 0, int(cap_units), _ptr(cnt, _pi32), _ptr(act, _pu8), _ptr(kept, _pu8))
+    return cnt, act, kept
 
 
 def num_threads() -> int:

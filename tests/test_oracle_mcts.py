@@ -256,3 +256,29 @@ def test_virtual_loss_definition_on_live_reference_matches_c():
                                   leaves=4)
     c0, w0, p0 = m.root_stats()
     assert np.array_equal(cnt[0], c0) and np.array_equal(W[0], w0) and np.array_equal(P[0], p0)
+
+
+@pytest.mark.parametrize("leaves", [1, 4])
+@pytest.mark.parametrize("cap", [None, 120])
+def test_tree_reuse_c_restatement_matches_the_python_definition(leaves, cap):
+    """MCTS.advance (keep the subtree of the move played iff expanded and within the cap; the next search adds to its
+    statistics) against orc_mcts_advance / orc_mcts_play_hash: same visit counts and moves at every ply of a game."""
+    game = mr.ReversiGame(po.OracleReversiBoard, 6)
+    salt = 5
+    hist, _ = mr.self_play_game(game, 32, 1.25, lambda a, b: mr.hash_eval(a, b, salt, 65), max_plies=14, leaves=leaves,
+                                reuse=True, cap_units=cap)
+    b, p = game.initial()
+    me, opp = game.wire(b, p)
+    cnt, act, kept = po.play_hash([me], [opp], 32, 14, size=6, salt=salt, leaves=leaves, reuse=True,
+                                  cap_units=-1 if cap is None else cap)
+    assert len(hist) == 14
+    for i, h in enumerate(hist):
+        assert np.array_equal(h[3], cnt[0, i]) and h[4] == act[0, i], i
+    assert kept[0].sum() >= 6  # most moves continue on a kept subtree ...
+    assert any(int(c.sum()) > 32 for c in cnt[0])  # ... whose root carries more than one search's visits
+    if cap is not None:
+        assert kept[0].sum() < 14  # the cap drops the large ones
+    # without reuse the same driver reproduces the fresh-tree games
+    hist0, _ = mr.self_play_game(game, 32, 1.25, lambda a, b: mr.hash_eval(a, b, salt, 65), max_plies=6, leaves=leaves)
+    cnt0, act0, kept0 = po.play_hash([me], [opp], 32, 6, size=6, salt=salt, leaves=leaves)
+    assert all(np.array_equal(h[3], cnt0[0, i]) and h[4] == act0[0, i] for i, h in enumerate(hist0)) and not kept0.any()
