@@ -78,6 +78,7 @@ SIGNATURES = {
     "bz_selfplay_init": [_SP, _I64, ptr],
     "bz_selfplay_advance": [_SP, _PP, ptr, ptr],
     "bz_reversi_symmetry": [ptr, ptr, ptr, ptr, ptr, ptr, ptr, _I64, _INT, ptr],
+    "bz_record_hash": [ptr, ptr, ptr, ptr, _I64, ptr],
     "bz_philox_u32": [_U64, ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_forward_pair": [ptr, ptr, ptr, _I64, ptr],
     "bz_mlp_pair_image_bytes": [],

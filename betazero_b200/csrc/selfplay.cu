@@ -233,6 +233,29 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// 64-bit content hash of a (board, pi) record: the dedup key of the dataset expansion (a warp per record)
+__device__ __forceinline__ uint64_t rec_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+    record_hash_kernel(const uint64_t *__restrict__ me, const uint64_t *__restrict__ opp, const float *__restrict__ pi,
+                       uint64_t *__restrict__ out, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const float *row = pi + i * A;
+        uint64_t h = 0;
+        for (int a = lane; a < A; a += 32) {
+            const float f = row[a];
+            const uint32_t bits = f == 0.f ? 0u : __float_as_uint(f);  // -0 == +0, as in a value comparison
+            h += rec_mix(((uint64_t)(a + 1) << 32) | bits);           // order-independent sum of per-cell hashes
+        }
+        for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(kFull, h, d);
+        if (lane == 0) out[i] = rec_mix(h ^ rec_mix(me[i] + 0x9E3779B97F4A7C15ULL) ^ rec_mix(opp[i] * 0xD1B54A32D192ED03ULL + 1));
+    }
+}
+
 int check_state(const bz_selfplay_state *s) {
     if (!s) return BZ_ERR_ARG;
     if (!(s->board_size == 4 || s->board_size == 6 || s->board_size == 8)) return BZ_ERR_ARG;
@@ -282,6 +305,13 @@ int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi
     if (n == 0) return BZ_OK;
     symmetry_kernel<<<persistent_grid(n * A, 256, 8), 256, 0, as_stream(stream)>>>(me, opp, pi, sym, me_out, opp_out,
                                                                                 pi_out, n, size);
+    return launch_rc();
+}
+
+int bz_record_hash(const uint64_t *me, const uint64_t *opp, const float *pi, uint64_t *hash_out, int64_t n, bz_stream_t stream) {
+    if (n < 0 || (n && (!me || !opp || !pi || !hash_out))) return BZ_ERR_ARG;
+    if (n == 0) return BZ_OK;
+    record_hash_kernel<<<persistent_grid(n * 32, 256, 8), 256, 0, as_stream(stream)>>>(me, opp, pi, hash_out, n);
     return launch_rc();
 }
 

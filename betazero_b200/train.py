@@ -28,6 +28,49 @@ def augment(me: torch.Tensor, opp: torch.Tensor, pi: torch.Tensor, sym: torch.Te
     return me_o, opp_o, pi_o
 
 
+REFERENCE_TRANSFORMS = (0, 1, 2, 3, 4, 5, 6, 5)  # the reference's eight lambdas: its 8th, flip(0).t(), IS rot90 x3 (train.py:35)
+
+
+def expand_with_transforms(me: torch.Tensor, opp: torch.Tensor, pi: torch.Tensor, z: torch.Tensor | None = None, size: int = 8,
+                           dedup: bool = True, transforms=tuple(range(8))):
+    """The reference's dataset expansion (``TicTacToeDataset.expand_with_transforms``, SL/train.py:23-50) for (board, pi)
+    records: every record under the eight transforms, record-major / transform-minor like the reference's two loops, and
+    -- ``dedup`` -- only the FIRST occurrence of every distinct (state, action) pair is kept (its ``unique_data`` set).
+    ``transforms``: the engine's eight distinct dihedral transforms, or ``REFERENCE_TRANSFORMS`` for the reference's own
+    list, whose 8th entry duplicates the 6th and therefore never survives the dedup.
+    Returns (me, opp, pi[, z]) of the kept records in that order, and the index of the source record of each."""
+    n, T = me.numel(), len(transforms)
+    dev = me.device
+    src = torch.arange(n, device=dev).repeat_interleave(T)
+    sym = torch.tensor(list(transforms), dtype=torch.uint8, device=dev).repeat(n)
+    me8, opp8, pi8 = augment(me[src].contiguous(), opp[src].contiguous(), pi[src].contiguous(), sym, size)
+    if dedup and n:
+        h = torch.empty(n * T, dtype=torch.int64, device=dev)
+        L = _lib.load()
+        _lib.check(L.bz_record_hash(_lib.dptr(me8), _lib.dptr(opp8), _lib.dptr(pi8), _lib.dptr(h), n * T, _lib.stream_ptr()),
+                   "bz_record_hash")
+        order = torch.argsort(h, stable=True)  # equal records become neighbours, in their original order
+        hs = h[order]
+        same_hash = hs[1:] == hs[:-1]
+        a, b = order[1:], order[:-1]
+        same_rec = same_hash & (me8[a] == me8[b]) & (opp8[a] == opp8[b]) & (pi8[a] == pi8[b]).all(dim=1)
+        if bool((same_hash & ~same_rec).any()):
+            # two different records share a 64-bit hash (never seen; ~1e-8 for millions of records): equal records may
+            # then not be neighbours -- fall back to an exact row-wise unique
+            rows = torch.cat([me8[:, None], opp8[:, None], pi8.view(torch.int32).long()], dim=1)
+            _, inv = torch.unique(rows, dim=0, return_inverse=True)
+            first = torch.full((int(inv.max()) + 1,), n * T, dtype=torch.int64, device=dev).scatter_reduce(
+                0, inv, torch.arange(n * T, device=dev), reduce="amin")
+            keep = torch.zeros(n * T, dtype=torch.bool, device=dev)
+            keep[first] = True
+        else:
+            keep = torch.ones(n * T, dtype=torch.bool, device=dev)
+            keep[a[same_rec]] = False  # a later copy of its predecessor in the run
+        me8, opp8, pi8, src = me8[keep], opp8[keep], pi8[keep], src[keep]
+    out = (me8, opp8, pi8) + ((z[src],) if z is not None else ())
+    return out + (src,)
+
+
 def make_batch(replay: dict, idx: torch.Tensor, size: int = 8, augment_seed: int | None = None):
     """(planes bf16 [b,2,8,8], pi f32 [b,65], z f32 [b]) for the records ``idx`` of a replay dict."""
     me, opp = replay["me"][idx].contiguous(), replay["opp"][idx].contiguous()

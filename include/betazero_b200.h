@@ -343,6 +343,12 @@ int bz_reversi_symmetry(const uint64_t *me, const uint64_t *opp, const float *pi
                         uint64_t *me_out, uint64_t *opp_out, float *pi_out, int64_t n, int size,
                         bz_stream_t stream);
 
+/* 64-bit content hash of every (board, pi) record (me, opp, float32 pi[65]; -0 hashes like +0): the dedup key of the
+ * dataset expansion -- the reference keeps the first occurrence of every distinct (state, action) pair of its 8-fold
+ * expanded dataset (src/tic_tac_toe/SL/train.py:38-50, a string set); betazero_b200.train.expand_with_transforms sorts
+ * by this key and compares the records themselves, so a hash collision cannot merge two different records. */
+int bz_record_hash(const uint64_t *me, const uint64_t *opp, const float *pi, uint64_t *hash_out, int64_t n, bz_stream_t stream);
+
 /* Fused policy/value MLP inference (the network is the only dense contraction on the path and the
  * only tensor-core user): x bf16 [n, 128] canonical planes -> 128 -> 256 -> 256 -> 256 (ReLU) ->
  * head, all four layers in ONE tcgen05/TMEM kernel launch.  Architecture = the reference's TicTacToeNet

@@ -145,3 +145,68 @@ def test_one_iteration_of_the_alphazero_loop(tmp_path, leaves):
     for a, b in zip(st.model.parameters(), st2.model.parameters()):
         assert torch.equal(a, b)
     assert train.load_checkpoint(ck, st2.master) == 2
+
+
+def _dense(me, opp, pi, size):
+    """(state [size, size] of +1 / -1 / 0, action [size, size], pass prior) of one record, like the reference's State / Action"""
+    st = torch.zeros((8, 8))
+    for b in range(64):
+        if (me >> b) & 1:
+            st[b >> 3, b & 7] = 1.0
+        elif (opp >> b) & 1:
+            st[b >> 3, b & 7] = -1.0
+    return st[:size, :size].clone(), pi[:64].reshape(8, 8)[:size, :size].clone(), float(pi[64])
+
+
+@pytest.mark.parametrize("size", [8, 6])
+@pytest.mark.parametrize("reference_list", [False, True])
+def test_expand_with_transforms_keeps_the_first_of_every_distinct_pair_like_the_reference(size, reference_list):
+    """SL/train.py:23-50: every record under the eight lambdas, a (state string, action string) set keeps the first
+    occurrence.  Restated here on dense tensors with the reference's own lambdas; the engine must keep the same
+    (record, transform) pairs in the same order, with the same contents."""
+    from betazero_b200 import env, train
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(size)
+    n = 60
+    me_h, opp_h = po.playout_boards(n, seed=5, size=size)
+    start = po.grid_to_wire(po.OracleReversiBoard(size=size).board, 1)
+    me_h[:6], opp_h[:6] = start[0], start[1]  # symmetric positions: transforms coincide
+    me_h[10:14], opp_h[10:14] = me_h[20:24], opp_h[20:24]  # repeated records
+    pi_h = np.zeros((n, 65), np.float32)
+    for i in range(n):
+        cells = [r * 8 + c for r in range(size) for c in range(size) if not ((int(me_h[i]) | int(opp_h[i])) >> (r * 8 + c)) & 1]
+        pick = rng.choice(cells, size=min(3, len(cells)), replace=False) if cells else []
+        for a in pick:
+            pi_h[i, a] = rng.integers(1, 5) / 8.0
+        pi_h[i, 64] = 0.125 if i % 7 == 0 else 0.0
+    pi_h[:6] = 0
+    pi_h[:6, 64] = 1.0  # fully symmetric records: all eight transforms are one pair
+    pi_h[10:14] = pi_h[20:24]
+    lambdas = [lambda x: x, lambda x: x.flip(dims=[0]), lambda x: x.flip(dims=[1]), lambda x: x.rot90(1, [0, 1]),
+               lambda x: x.rot90(2, [0, 1]), lambda x: x.rot90(3, [0, 1]), lambda x: x.t(),
+               (lambda x: x.flip(dims=[0]).t()) if reference_list else (lambda x: x.flip(dims=[0, 1]).t())]
+    seen, expect = set(), []
+    for i in range(n):
+        st, ac, ps = _dense(int(me_h[i]), int(opp_h[i]), torch.from_numpy(pi_h[i]), size)
+        for k, f in enumerate(lambdas):
+            ts, ta = f(st), f(ac)
+            key = (",".join(map(str, ts.reshape(-1).tolist())), ",".join(map(str, ta.reshape(-1).tolist())), ps)
+            if key not in seen:
+                seen.add(key)
+                expect.append((i, ts, ta))
+    me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
+    pi = torch.from_numpy(pi_h).cuda()
+    z = torch.arange(n, dtype=torch.int8, device="cuda")
+    tf = train.REFERENCE_TRANSFORMS if reference_list else tuple(range(8))
+    me8, opp8, pi8, z8, src = train.expand_with_transforms(me, opp, pi, z, size=size, transforms=tf)
+    assert src.cpu().tolist() == [e[0] for e in expect]
+    assert torch.equal(z8.cpu(), z.cpu()[src.cpu()])
+    mh, oh, ph = env.to_host_u64(me8), env.to_host_u64(opp8), pi8.cpu()
+    for j, (i, ts, ta) in enumerate(expect):
+        st, ac, ps = _dense(int(mh[j]), int(oh[j]), ph[j], size)
+        assert torch.equal(st, ts) and torch.equal(ac, ta) and ps == float(pi_h[i, 64]), (j, i)
+    if reference_list:
+        assert len(expect) <= 7 * n  # the reference's 8th lambda never adds a record
+    full = train.expand_with_transforms(me, opp, pi, size=size, dedup=False)
+    assert full[0].numel() == 8 * n and len(expect) < 8 * n
