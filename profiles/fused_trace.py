@@ -7,6 +7,10 @@ import torch
 from betazero_b200 import _lib, env, mcts, net as netmod
 B, S = int(os.environ.get("GAMES", "4096")), 800
 model = netmod.make_net("mlp", seed=0)
+if os.environ.get("LOGIT_SCALE"):  # sharpened priors: deeper trees (bench.py depth_sweep)
+    with torch.no_grad():
+        model.policy.weight.mul_(float(os.environ["LOGIT_SCALE"]))
+        model.policy.bias.mul_(float(os.environ["LOGIT_SCALE"]))
 me, opp, _ = env.reversi_init(B)
 L = _lib.load()
 s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False)
@@ -14,6 +18,7 @@ for _ in range(2):
     s.reset(me, opp)
     _lib.check(L.bz_mcts_search_fused(s.pools._ref, _lib.dptr(model._image_pair), _lib.dptr(s.prior_w), S // 4, _lib.stream_ptr()), "fused")
 torch.cuda.synchronize()
+print("stats", s.stats())
 t = np.zeros(96, np.int64)
 L.bz_fused_debug_trace.argtypes = [ctypes.c_void_p]
 assert L.bz_fused_debug_trace(t.ctypes.data) == 0
