@@ -430,6 +430,57 @@ class BatchedMCTS:
             self.check_errors()
         return out
 
+    def search_host(self, root_me: torch.Tensor, root_opp: torch.Tensor, n_sims: int):
+        """The host-facing form of :meth:`search` (``Player.get_move`` for a batch of boards that live in HOST memory):
+        roots from host tensors -> pinned staging -> H2D -> fresh search -> pi + most visited action -> D2H, one stream
+        synchronisation.  Returns ``(pi float32 [B, A], action uint8 [B])`` as pinned host tensors that stay valid until the
+        next call.  With the one-launch search (and no root noise) the whole sequence -- copies, reset, search, policy
+        kernels -- is captured once in a CUDA graph and replayed: one launch from the host per call instead of eight."""
+        p = self.pools
+        B, A = max(p.n_trees, 1), p.n_actions
+        if root_me.numel() != p.n_trees or root_opp.numel() != p.n_trees:
+            raise ValueError("one root per tree expected")
+        st = getattr(self, "_host", None)
+        if st is None:
+            st = self._host = {
+                "h_me": torch.empty(B, dtype=torch.int64).pin_memory(), "h_opp": torch.empty(B, dtype=torch.int64).pin_memory(),
+                "d_me": torch.empty(B, dtype=torch.int64, device=p.device), "d_opp": torch.empty(B, dtype=torch.int64, device=p.device),
+                "h_pi": torch.empty((B, A), dtype=torch.float32).pin_memory(), "h_act": torch.empty(B, dtype=torch.uint8).pin_memory(),
+                "graphs": {}}
+        st["h_me"][: p.n_trees].copy_(root_me.reshape(-1))
+        st["h_opp"][: p.n_trees].copy_(root_opp.reshape(-1))
+
+        def body():
+            st["d_me"].copy_(st["h_me"], non_blocking=True)
+            st["d_opp"].copy_(st["h_opp"], non_blocking=True)
+            self.reset(st["d_me"][: p.n_trees], st["d_opp"][: p.n_trees])
+            self.run(n_sims)
+            _, pi, _ = self.root_policy()
+            act = self.best_action()
+            st["h_pi"].copy_(pi, non_blocking=True)
+            st["h_act"].copy_(act, non_blocking=True)
+
+        if self.one_launch and self.dirichlet_alpha == 0 and p.n_trees > 0:
+            g = st["graphs"].get(n_sims)
+            if g is None:
+                n0 = self.launches
+                body()  # once eagerly: lazy initialisation (sqrt table, shared-memory opt-in) must not happen under capture
+                torch.cuda.current_stream().synchronize()
+                per_call = self.launches - n0
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body()
+                self.launches = n0
+                st["graphs"][n_sims] = (g, per_call)
+                g = st["graphs"][n_sims]
+            g[0].replay()
+            self.launches += g[1]
+        else:
+            body()
+        torch.cuda.current_stream().synchronize()
+        self.check_errors()
+        return st["h_pi"], st["h_act"]
+
     def root_policy(self):
         p = self.pools
         _lib.check(self._L.bz_mcts_root_policy(p._ref, _lib.dptr(self.counts), _lib.dptr(self.pi), _lib.dptr(self.q),

@@ -166,3 +166,22 @@ def test_selfplay_games_are_identical_with_the_one_launch_search():
     assert recs[0][0] == recs[1][0]
     for k in recs[0][1]:
         assert torch.equal(recs[0][1][k], recs[1][1][k]), k
+
+
+@pytest.mark.parametrize("one", [True, False])
+def test_search_host_returns_the_policy_and_move_of_a_fresh_search(one):
+    """BatchedMCTS.search_host (host roots in, pinned pi + move out; with the one-launch search a replayed CUDA graph)
+    against search() + best_action(), over several calls with different roots."""
+    from betazero_b200 import mcts, net
+
+    model = net.make_net("mlp", seed=6)
+    B, n_sims = 200, 48
+    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False, one_launch=one)
+    ref = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False, one_launch=False)
+    for seed in (1, 2, 3):
+        me, opp = _roots(B, seed)
+        h_pi, h_act = s.search_host(me.cpu(), opp.cpu(), n_sims)
+        _, pi, _ = ref.search(me, opp, n_sims)
+        act = ref.best_action()
+        assert torch.equal(h_pi, pi.cpu()) and torch.equal(h_act, act.cpu())
+        assert h_pi.is_pinned() and h_act.is_pinned()
