@@ -19,11 +19,11 @@ def _roots(B, seed, start=False):
     return env.to_device_u64(me_h), env.to_device_u64(opp_h)
 
 
-def _search(model, me, opp, n_sims, one_launch, **kw):
+def _search(model, me, opp, n_sims, one_launch, n_leaves=4, **kw):
     from betazero_b200 import mcts
 
     B = me.numel()
-    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False,
+    s = mcts.BatchedMCTS(mcts.TreePools(B, n_sims, n_leaves=n_leaves), mcts.FusedNetEvaluator(model), use_graph=False,
                          one_launch=one_launch, **kw)
     assert s.one_launch is bool(one_launch)
     s.pools.arena.zero_()  # the padding words at the end of a node block are never written: make them comparable
@@ -56,6 +56,33 @@ def test_one_launch_search_builds_the_same_trees(B):
     me, opp = _roots(B, seed=100 + B)
     n_sims = 64 if B <= 300 else 32
     _same_trees(_search(model, me, opp, n_sims, True), _search(model, me, opp, n_sims, False))
+
+
+@pytest.mark.parametrize("B,n_sims", [(1, 40), (29, 64), (300, 64), (4144, 16), (4500, 16)])
+def test_one_launch_search_with_one_leaf_per_iteration_builds_the_same_trees(B, n_sims):
+    """the sequential definition (one descent per tree and iteration, a full warp per tree) through search_fused_kernel<1>"""
+    from betazero_b200 import net
+
+    model = net.make_net("mlp", seed=B + 1)
+    me, opp = _roots(B, seed=200 + B)
+    _same_trees(_search(model, me, opp, n_sims, True, n_leaves=1), _search(model, me, opp, n_sims, False, n_leaves=1))
+
+
+def test_one_launch_one_leaf_headline_size_and_deep_trees():
+    from betazero_b200 import net
+
+    model = net.make_net("mlp", seed=0)
+    me, opp = _roots(4096, 0, start=True)
+    a, b = _search(model, me, opp, 200, True, n_leaves=1), _search(model, me, opp, 200, False, n_leaves=1)
+    _same_trees(a, b)
+    assert int(a.root_edges()[0][0].sum()) == 199  # the first iteration expands the root
+    with torch.no_grad():  # peaked priors: paths deeper than the 32 entries a warp keeps in registers
+        model.policy.weight.mul_(512)
+        model.policy.bias.mul_(512)
+    me, opp = _roots(256, 0, start=True)
+    a, b = _search(model, me, opp, 600, True, n_leaves=1), _search(model, me, opp, 600, False, n_leaves=1)
+    _same_trees(a, b)
+    assert a.stats()["mean_depth"] > 20.0
 
 
 def test_one_launch_headline_config_4096_trees_800_sims():
@@ -133,7 +160,7 @@ def test_one_launch_is_refused_outside_its_shape():
     model = net.make_net("mlp", seed=1)
     big = mcts.BatchedMCTS(mcts.TreePools(4145, 8, n_leaves=4, arena_units=64), mcts.FusedNetEvaluator(model), use_graph=False)
     assert big.one_launch  # more than one launch's 4144 trees: searched in chunks
-    for kw in (dict(n_leaves=2), dict(n_leaves=1), dict(n_leaves=4, group_lanes=8)):
+    for kw in (dict(n_leaves=2), dict(n_leaves=3), dict(n_leaves=4, group_lanes=8)):
         s = mcts.BatchedMCTS(mcts.TreePools(64, 8, **kw), mcts.FusedNetEvaluator(model), use_graph=False)
         assert not s.one_launch
     with pytest.raises(RuntimeError):
