@@ -275,6 +275,10 @@ class BatchedMCTS:
         if self._one_launch_arg is False:
             return False
         ok = self.one_launch_ok()
+        if self._one_launch_arg is None and ok and self.pools.n_leaves == 1 and self.pools.n_trees > self.ONE_LAUNCH_MAX_TREES:
+            # one leaf per iteration and more trees than one launch holds: the per-iteration kernels with 16 / 8 lanes per
+            # tree fill the GPU better than chunks of 4144 one after the other (65 536 trees: 776 M against ~320 M sims/s)
+            return False
         if self._one_launch_arg and not ok:
             raise RuntimeError("one_launch=True, but bz_mcts_search_fused does not cover this search (it needs Reversi, "
                                "n_leaves = 1 or n_leaves = 4 in wave mode, and the bf16 MLP kernel path)")
