@@ -231,11 +231,12 @@ int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *
  * trees in two islands; while one island's leaves are in the net (tcgen05 cta_group::2, the weight image of
  * bz_mlp_forward_pair resident in shared memory for the whole search, the leaf planes written from registers into the
  * A operand) the other island's warps walk their trees.
- * Shape: Reversi, n_leaves == 4 in wave mode (group_lanes 0 or 32), prior_mode BZ_PRIOR_LOGITS_BF16 with
+ * Shape: Reversi; n_leaves == 4 in wave mode (group_lanes 0 or 32) or n_leaves <= 1 (the sequential one-leaf search: a
+ * warp per tree here whatever group_lanes says -- the trees do not depend on it); prior_mode BZ_PRIOR_LOGITS_BF16 with
  * eval_stride == 72 (BZ_ERR_ARG otherwise: use the per-iteration entry points).  One launch holds 148 * 28 = 4144
  * trees; more trees are searched in equal chunks, one launch after the other on the stream.
  * eval_out: ignored (may be NULL; earlier versions used it as scratch -- the net's rows now stay in shared memory);
- * leaf_planes is not written.  n_iterations = simulations per tree / 4. */
+ * leaf_planes is not written.  n_iterations = simulations per tree / max(n_leaves, 1). */
 int bz_mcts_search_fused(const bz_tree_pools *pools, const void *weight_image_pair, void *eval_out, int n_iterations,
                          bz_stream_t stream);
 
