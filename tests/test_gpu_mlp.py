@@ -74,7 +74,7 @@ def test_search_with_fused_mlp_kernel_agrees_with_library_gemms():
     for fused in (True, False):
         ev = mcts.FusedNetEvaluator(model, use_kernel=fused)
         pools = mcts.TreePools(B, n_sims)
-        s = mcts.BatchedMCTS(pools, ev, use_graph=True, graph_unroll=8)
+        s = mcts.BatchedMCTS(pools, ev, use_graph=True, graph_unroll=8, one_launch=False)  # the per-iteration path
         cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
         _, _, P = s.root_edges()
         res.append((cnt.cpu().numpy(), P.cpu().numpy()))
@@ -96,7 +96,8 @@ def test_programmatic_dependent_launch_changes_nothing_but_time():
     try:
         for pdl in (False, True):
             pools = mcts.TreePools(B, n_sims)
-            s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=True, pdl=pdl), use_graph=True, graph_unroll=8)
+            s = mcts.BatchedMCTS(pools, mcts.FusedNetEvaluator(model, use_kernel=True, pdl=pdl), use_graph=True, graph_unroll=8,
+                                 one_launch=False)  # the per-iteration path is the one that chains two kernels
             cnt, pi, q = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), n_sims)
             out.append((cnt.clone(), q.clone()))
     finally:
@@ -114,8 +115,8 @@ def test_pdl_flag_does_not_leak_into_searches_without_a_kernel_between_steps():
     me_h, opp_h = po.playout_boards(B, seed=5)
     me, opp = env.to_device_u64(me_h), env.to_device_u64(opp_h)
     model = net.make_net("mlp", seed=7)
-    s0 = mcts.BatchedMCTS(mcts.TreePools(B, n_sims), mcts.FusedNetEvaluator(model), graph_unroll=8)
-    s0.search(me, opp, n_sims)
+    s0 = mcts.BatchedMCTS(mcts.TreePools(B, n_sims), mcts.FusedNetEvaluator(model), graph_unroll=8, one_launch=False)
+    s0.search(me, opp, n_sims)  # the per-iteration path: MLP kernel and step kernel chained with the launch attribute
     assert _lib._pdl_state is True
 
     class Static:  # fixed logits, no kernel of its own
