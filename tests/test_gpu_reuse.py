@@ -197,3 +197,37 @@ def test_reference_style_players_with_reuse_follow_the_definition(leaves):
                 orc[s].advance(a, ob, nxt, gpu[s].pools.reuse_cap_units)
         player = nxt
     assert kept_moves >= 4
+
+
+@pytest.mark.parametrize("leaves", [1, 2])
+def test_tree_reuse_on_tic_tac_toe_matches_the_oracle(leaves):
+    """bz_mcts_reroot is game-agnostic (it moves node blocks): config-1 style tic-tac-toe play from the empty board and
+    from a few two-ply positions, every move's visit counts against orc_mcts_play_hash with reuse"""
+    from betazero_b200 import mcts
+    from oracle import pyoracle as po
+
+    starts = [(0, 0), (1 << 4, 1 << 0), (1 << 0, 1 << 8), (1 << 2, 1 << 4), (1 << 7, 1 << 1)]  # (me, opp): X to move
+    me_h = np.array([s[0] for s in starts], np.uint64)
+    opp_h = np.array([s[1] for s in starts], np.uint64)
+    B, n_sims, plies, salt = len(starts), 40, 5, 3
+    cnt_o, act_o, kept_o = po.play_hash(me_h, opp_h, n_sims, plies, game=po.GAME_TTT, salt=salt, leaves=leaves, reuse=True)
+    pools = mcts.TreePools(B, n_sims, game=mcts.GAME_TTT, n_leaves=leaves, reuse=True)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(salt), use_graph=False)
+    me = torch.from_numpy(me_h.view(np.int64)).cuda()
+    opp = torch.from_numpy(opp_h.view(np.int64)).cuda()
+    s.reset(me, opp)
+    alive = np.ones(B, bool)
+    for p in range(plies):
+        s.run(n_sims)
+        s.check_errors()
+        counts = s.root_policy()[0].cpu().numpy()
+        alive &= act_o[:, p] != 255  # games that have ended: the oracle stops, the engine searches a terminal root
+        assert np.array_equal(counts[alive], cnt_o[alive, p]), p
+        a = s.best_action().clone()
+        assert np.array_equal(a.cpu().numpy()[alive], act_o[alive, p])
+        bit = torch.where(a < 9, torch.ones_like(me) << a.long().clamp(max=8), torch.zeros_like(me))
+        me, opp = opp.clone(), (me | bit)  # the mover's mark is placed, the view flips to the next mover
+        s.advance(a, me, opp)
+        kept = (pools.inherited > 0).cpu().numpy()
+        assert np.array_equal(kept[alive], kept_o[alive, p].astype(bool)), p
+    assert kept_o.sum() > 0
