@@ -234,7 +234,7 @@ class BatchedMCTS:
                  one_launch: bool | None = None):
         self.pools, self.evaluator = pools, evaluator
         # one_launch: run the whole search of a move in ONE kernel (bz_mcts_search_fused) when the shape allows --
-        # Reversi, one leaf per iteration or 4 in wave mode, the bf16 MLP through its tcgen05 kernel path (more than 4144
+        # Reversi, one leaf per iteration or 2 / 4 in wave mode, the bf16 MLP through its tcgen05 kernel path (more than 4144
         # trees are searched in chunks, one launch each).
         # None = whenever possible; False = always the per-iteration kernels; True = raise if the shape does not fit.
         self._one_launch_arg = one_launch
@@ -267,7 +267,7 @@ class BatchedMCTS:
         net = getattr(ev, "net", None)
         return (isinstance(ev, FusedNetEvaluator) and ev.use_kernel is not False and getattr(ev, "own_launches", 0) == 1
                 and getattr(net, "_image_pair", None) is not None and self.fused
-                and p.game == GAME_REVERSI and ((p.n_leaves == 4 and p.group_lanes in (0, 32)) or p.n_leaves == 1)
+                and p.game == GAME_REVERSI and ((p.n_leaves in (2, 4) and p.group_lanes in (0, 32)) or p.n_leaves == 1)
                 and p.prior_mode == PRIOR_LOGITS_BF16 and p.eval_stride == 72 and p.n_trees > 0)
 
     @property
@@ -281,7 +281,7 @@ class BatchedMCTS:
             return False
         if self._one_launch_arg and not ok:
             raise RuntimeError("one_launch=True, but bz_mcts_search_fused does not cover this search (it needs Reversi, "
-                               "n_leaves = 1 or n_leaves = 4 in wave mode, and the bf16 MLP kernel path)")
+                               "n_leaves = 1 or n_leaves = 2 / 4 in wave mode, and the bf16 MLP kernel path)")
         return ok
 
     def search_one_launch(self, n_iterations: int) -> None:

@@ -231,7 +231,7 @@ int bz_mcts_step(const bz_tree_pools *pools, const void *eval_out, const float *
  * trees in two islands; while one island's leaves are in the net (tcgen05 cta_group::2, the weight image of
  * bz_mlp_forward_pair resident in shared memory for the whole search, the leaf planes written from registers into the
  * A operand) the other island's warps walk their trees.
- * Shape: Reversi; n_leaves == 4 in wave mode (group_lanes 0 or 32) or n_leaves <= 1 (the sequential one-leaf search: a
+ * Shape: Reversi; n_leaves == 2 or 4 in wave mode (group_lanes 0 or 32) or n_leaves <= 1 (the sequential one-leaf search: a
  * warp per tree here whatever group_lanes says -- the trees do not depend on it); prior_mode BZ_PRIOR_LOGITS_BF16 with
  * eval_stride == 72 (BZ_ERR_ARG otherwise: use the per-iteration entry points).  One launch holds 148 * 28 = 4144
  * trees; more trees are searched in equal chunks, one launch after the other on the stream.

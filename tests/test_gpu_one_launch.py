@@ -68,6 +68,31 @@ def test_one_launch_search_with_one_leaf_per_iteration_builds_the_same_trees(B, 
     _same_trees(_search(model, me, opp, n_sims, True, n_leaves=1), _search(model, me, opp, n_sims, False, n_leaves=1))
 
 
+@pytest.mark.parametrize("B,n_sims", [(1, 40), (57, 64), (300, 96), (4144, 16), (4500, 16)])
+def test_one_launch_search_with_two_leaves_per_iteration_builds_the_same_trees(B, n_sims):
+    """two virtual-loss descents per tree and iteration (16 lanes each) through search_fused_kernel<2>"""
+    from betazero_b200 import net
+
+    model = net.make_net("mlp", seed=B + 2)
+    me, opp = _roots(B, seed=300 + B)
+    _same_trees(_search(model, me, opp, n_sims, True, n_leaves=2), _search(model, me, opp, n_sims, False, n_leaves=2))
+
+
+def test_one_launch_two_leaves_headline_size_and_deep_trees():
+    from betazero_b200 import net
+
+    model = net.make_net("mlp", seed=0)
+    me, opp = _roots(4096, 0, start=True)
+    _same_trees(_search(model, me, opp, 400, True, n_leaves=2), _search(model, me, opp, 400, False, n_leaves=2))
+    with torch.no_grad():  # peaked priors: paths deeper than the 16 entries a slot keeps in registers
+        model.policy.weight.mul_(512)
+        model.policy.bias.mul_(512)
+    me, opp = _roots(256, 0, start=True)
+    a, b = _search(model, me, opp, 600, True, n_leaves=2), _search(model, me, opp, 600, False, n_leaves=2)
+    _same_trees(a, b)
+    assert a.stats()["mean_depth"] > 18.0
+
+
 def test_one_launch_one_leaf_headline_size_and_deep_trees():
     from betazero_b200 import net
 
@@ -160,15 +185,15 @@ def test_one_launch_is_refused_outside_its_shape():
     model = net.make_net("mlp", seed=1)
     big = mcts.BatchedMCTS(mcts.TreePools(4145, 8, n_leaves=4, arena_units=64), mcts.FusedNetEvaluator(model), use_graph=False)
     assert big.one_launch  # more than one launch's 4144 trees: searched in chunks
-    for kw in (dict(n_leaves=2), dict(n_leaves=3), dict(n_leaves=4, group_lanes=8)):
+    for kw in (dict(n_leaves=8), dict(n_leaves=3), dict(n_leaves=4, group_lanes=8), dict(n_leaves=2, group_lanes=16)):
         s = mcts.BatchedMCTS(mcts.TreePools(64, 8, **kw), mcts.FusedNetEvaluator(model), use_graph=False)
         assert not s.one_launch
     with pytest.raises(RuntimeError):
-        mcts.BatchedMCTS(mcts.TreePools(64, 8, n_leaves=2), mcts.FusedNetEvaluator(model), one_launch=True).one_launch
+        mcts.BatchedMCTS(mcts.TreePools(64, 9, n_leaves=3), mcts.FusedNetEvaluator(model), one_launch=True).one_launch
     assert not mcts.BatchedMCTS(mcts.TreePools(64, 8, n_leaves=4), mcts.HashEvaluator(1), use_graph=False).one_launch
     L = _lib.load()
-    p = mcts.TreePools(64, 8, n_leaves=2, prior_mode=mcts.PRIOR_LOGITS_BF16, eval_stride=72)
-    out = torch.zeros((128, 72), dtype=torch.bfloat16, device="cuda")
+    p = mcts.TreePools(64, 9, n_leaves=3, prior_mode=mcts.PRIOR_LOGITS_BF16, eval_stride=72)
+    out = torch.zeros((192, 72), dtype=torch.bfloat16, device="cuda")
     model.prepare_inference()
     assert L.bz_mcts_search_fused(p._ref, _lib.dptr(model._image_pair), _lib.dptr(out), 2, _lib.stream_ptr()) == -1  # BZ_ERR_ARG
 
