@@ -65,6 +65,9 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
             : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) return;
+#ifdef BZ_PARK_NS
+        __nanosleep(BZ_PARK_NS);
+#endif
     }
     __trap();
 }

@@ -5,6 +5,10 @@ import torch
 from betazero_b200 import _lib, env, mcts, net as netmod
 B, S = int(os.environ.get("GAMES", "4096")), int(os.environ.get("SIMS", "800"))
 model = netmod.make_net("mlp", seed=0)
+if os.environ.get("LOGIT_SCALE"):  # sharpened priors: deeper trees (bench.py depth_sweep)
+    with torch.no_grad():
+        model.policy.weight.mul_(float(os.environ["LOGIT_SCALE"]))
+        model.policy.bias.mul_(float(os.environ["LOGIT_SCALE"]))
 me, opp, _ = env.reversi_init(B)
 L = _lib.load()
 s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False)
