@@ -269,7 +269,11 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    roots_me = torch.empty((args.steps, B), dtype=torch.int64, device="cuda")  # the positions searched at every timed step
+    roots_opp = torch.empty_like(roots_me)                                     # (the e2e region searches the same ones)
     for _ in range(args.warmup):
+        roots_me[0].copy_(sp.me)  # the timed loop's own copies, so that nothing in it runs for the first time
+        roots_opp[0].copy_(sp.opp)
         sp.play_move()
     barrier()
 
@@ -279,8 +283,6 @@ def run_b200(args):
     barrier()
     sampler.window_begin()
     ev0.record()
-    roots_me = torch.empty((args.steps, B), dtype=torch.int64, device="cuda")  # the positions searched at every step
-    roots_opp = torch.empty_like(roots_me)                                     # (the e2e region searches the same ones)
     for i in range(args.steps):
         roots_me[i].copy_(sp.me)
         roots_opp[i].copy_(sp.opp)
