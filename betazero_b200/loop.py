@@ -29,7 +29,8 @@ from . import mcts, net, selfplay, train
 def default_args(**over) -> SimpleNamespace:
     """the command line's defaults as a namespace (for callers that drive iterations from Python: bench.py, tests)"""
     a = SimpleNamespace(games=4096, sims=800, leaves=4, plies=70, size=8, iterations=1, train_steps=8, batch=4096, lr=1e-4,
-                        temp_plies=8, net="mlp", hidden=256, seed=0, train_on_rank0=False, checkpoint=None, resume=None)
+                        temp_plies=8, net="mlp", hidden=256, seed=0, train_on_rank0=False, checkpoint=None, resume=None,
+                        reuse=False)
     for k, v in over.items():
         if not hasattr(a, k):
             raise TypeError(f"unknown loop argument {k!r}")
@@ -54,7 +55,7 @@ class LoopState:
                           else mcts.NetEvaluator(self.model))
         self.sp = selfplay.BatchedSelfPlay(args.games, args.sims, self.evaluator, board_size=args.size,
                                            temp_plies=args.temp_plies, seed=args.seed, rank=rank, world=world,
-                                           n_leaves=args.leaves,
+                                           n_leaves=args.leaves, reuse=bool(getattr(args, "reuse", False)),
                                            graph_unroll=min(16, max(1, args.sims // args.leaves - 1)))
         self.sp.prepare()
 
@@ -160,6 +161,8 @@ def main():
     ap.add_argument("--hidden", type=int, default=d.hidden)
     ap.add_argument("--seed", type=int, default=d.seed)
     ap.add_argument("--train-on-rank0", action="store_true")
+    ap.add_argument("--reuse", action="store_true", help="keep the searched subtree from move to move (bz_mcts_reroot): --sims "
+                                                         "NEW simulations per move on top of the kept ones")
     ap.add_argument("--checkpoint", default=None, help="write a state_dict checkpoint (master weights + Adam state) here "
                                                        "after every iteration (rank 0); SL/train.py:204-214")
     ap.add_argument("--resume", default=None, help="continue from a checkpoint written by --checkpoint")

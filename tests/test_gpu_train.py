@@ -111,6 +111,18 @@ def test_aiplayer_is_built_from_a_model_path(tmp_path):
             AIPlayer(p2, 1)
 
 
+def test_the_loop_runs_with_kept_trees():
+    """--reuse: self-play of the iteration loop continues every search on the subtree of the move played"""
+    from betazero_b200 import loop
+
+    args = loop.default_args(games=48, sims=16, leaves=4, plies=40, size=6, train_steps=2, batch=128, temp_plies=30, reuse=True)
+    st = loop.LoopState(args, rank=0, world=1)
+    assert st.sp.reuse and st.sp.pools.scratch is not None
+    line = loop.run_iteration(st, 0)
+    assert line["games_finished_local"] >= 48 and line["records_dropped_local"] == 0 and line["train_steps"] == 2
+    assert int(st.sp.pools.inherited.max()) > 0  # some root of the last search started with kept visits
+
+
 @pytest.mark.parametrize("leaves", [1, 4])
 def test_one_iteration_of_the_alphazero_loop(tmp_path, leaves):
     """BASELINE configs[4] on one GPU, small: full games with slot recycling, replay drain + (single-rank) gather,
