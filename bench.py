@@ -352,7 +352,7 @@ def run_b200(args):
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if one_launch:
-                same = B == 4096 and S == 800
+                same = B == 4096 and S == 800 and K == 4  # the configuration of the static capture
                 traffic = prof.get("search_fused_dram_bytes_per_launch") if same else None
                 winst = prof.get("search_fused_warp_inst_per_launch") if same else None
                 static_note = prof.get("search_fused_note")
