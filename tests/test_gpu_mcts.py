@@ -568,3 +568,24 @@ def test_virtual_loss_large_batch_stays_in_wave_mode():
     r_cnt, _, _, _ = po.search_hash(me_h[:256], opp_h[:256], S, po.GAME_REVERSI, 8, 1.25, 2, leaves=4)
     assert np.array_equal(cnt[:256], r_cnt)
     assert np.array_equal(cnt[256:512], r_cnt) and np.array_equal(cnt[-3:], r_cnt[(B - 3) % 256:][:3])
+
+
+@pytest.mark.parametrize("leaves", [1, 4])
+def test_visit_counts_beyond_the_sqrt_table(leaves):
+    """sqrt(n_node) comes from a 65536-entry table, and the straight-line scores are guarded by a vote that sends larger
+    counts (and out-of-range operands) through the exact forms: a 4x4 search long enough for nodes with more than 65536
+    visits (the small game tree saturates, most simulations end on known terminal nodes), bit for bit against the oracle."""
+    from betazero_b200 import env, mcts
+    from oracle import pyoracle as po
+
+    B, S = 6, 70000
+    me_h, opp_h = po.playout_boards(B, seed=3, size=4)
+    me_h[0], opp_h[0] = po.grid_to_wire(po.OracleReversiBoard(size=4).board, 1)
+    pools = mcts.TreePools(B, S, board_size=4, n_leaves=leaves, arena_units=400000)
+    s = mcts.BatchedMCTS(pools, mcts.HashEvaluator(2))
+    cnt, _, _ = s.search(env.to_device_u64(me_h), env.to_device_u64(opp_h), S)
+    r_cnt, r_W, r_P, _ = po.search_hash(me_h, opp_h, S, po.GAME_REVERSI, 4, 1.25, 2, leaves=leaves)
+    assert np.array_equal(cnt.cpu().numpy(), r_cnt)
+    assert int(r_cnt.max()) > 65536
+    W, P = _root_W_P(s)
+    assert np.array_equal(W, r_W) and np.array_equal(P, r_P)
