@@ -124,18 +124,22 @@ __device__ __forceinline__ void apply_legal(uint64_t &me, uint64_t &opp, unsigne
 // A whole warp: redux.sync.  Sub-warp groups: a redux with a different member mask per group is serialised group
 // by group (ncu: 12 % of the wave kernel's stall samples), so the groups use an xor butterfly over the full warp
 // instead (lane ^ d stays inside an aligned group of 8 or 16 lanes).  Every lane of the warp must call this together.
+// G: the group size as a compile-time constant (the butterfly is then straight-line code; as a loop over a run-time
+// popc(gmask) it was three trips with a branch each, on the critical path of every leaf)
+template <int G>
 __device__ __forceinline__ uint64_t group_or64(unsigned gmask, uint64_t v) {
     unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
-    if (gmask == 0xFFFFFFFFu) {
+    if (G == 32) {
         lo = __reduce_or_sync(0xFFFFFFFFu, lo);
         hi = __reduce_or_sync(0xFFFFFFFFu, hi);
     } else {
-        const int g = __popc(gmask);  // 8 or 16
-        for (int d = g >> 1; d; d >>= 1) {
+#pragma unroll
+        for (int d = G >> 1; d; d >>= 1) {
             lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, d);
             hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, d);
         }
     }
+    (void)gmask;
     return ((uint64_t)hi << 32) | lo;
 }
 
@@ -155,6 +159,7 @@ __device__ __forceinline__ int lane_shift(int gl) {
 }
 
 // discs flipped by the move on single-bit board x; every lane of the group returns the full set
+template <int G>
 __device__ __forceinline__ uint64_t group_flips(unsigned gmask, int gl, uint64_t x, uint64_t me, uint64_t opp) {
     const int s = lane_shift(gl);
     const bool rev = gl & 4;
@@ -165,7 +170,7 @@ __device__ __forceinline__ uint64_t group_flips(unsigned gmask, int gl, uint64_t
     f = (m & (f << s)) ? f : 0ULL;  // the run must end on a mover disc (reversi_board.py:56)
     if (rev) f = __brevll(f);
     if (gl >= 8) f = 0ULL;
-    return group_or64(gmask, f);
+    return group_or64<G>(gmask, f);
 }
 
 // candidate moves (before the empty-cell mask) of `gen` against `pro` in direction lane gl & 7
@@ -188,11 +193,11 @@ __device__ __forceinline__ void group_legal_masks(unsigned gmask, int gl, uint64
     if (G >= 16) {
         const bool second = gl & 8;
         const uint64_t mv = dir_moves(gl, second ? opp : me, second ? me : opp);
-        mask_me = group_or64(gmask, (gl < 8) ? mv : 0ULL) & empty;
-        mask_opp = group_or64(gmask, (gl >= 8 && gl < 16) ? mv : 0ULL) & empty;
+        mask_me = group_or64<G>(gmask, (gl < 8) ? mv : 0ULL) & empty;
+        mask_opp = group_or64<G>(gmask, (gl >= 8 && gl < 16) ? mv : 0ULL) & empty;
     } else {
-        mask_me = group_or64(gmask, dir_moves(gl, me, opp)) & empty;
-        mask_opp = group_or64(gmask, dir_moves(gl, opp, me)) & empty;
+        mask_me = group_or64<G>(gmask, dir_moves(gl, me, opp)) & empty;
+        mask_opp = group_or64<G>(gmask, dir_moves(gl, opp, me)) & empty;
     }
 }
 
@@ -202,9 +207,9 @@ __device__ __forceinline__ void group_legal_masks(unsigned gmask, int gl, uint64
 __device__ __forceinline__ void group8_legal_masks_lazy(unsigned gmask, int gl, uint64_t me, uint64_t opp, uint64_t cells,
                                                         bool want, uint64_t &mask_me, uint64_t &mask_opp) {
     const uint64_t empty = ~(me | opp) & cells;
-    mask_me = group_or64(gmask, dir_moves(gl, me, opp)) & empty;
+    mask_me = group_or64<8>(gmask, dir_moves(gl, me, opp)) & empty;
     mask_opp = 0;
-    if (__any_sync(0xFFFFFFFFu, want && mask_me == 0)) mask_opp = group_or64(gmask, dir_moves(gl, opp, me)) & empty;
+    if (__any_sync(0xFFFFFFFFu, want && mask_me == 0)) mask_opp = group_or64<8>(gmask, dir_moves(gl, opp, me)) & empty;
 }
 
 // ---- tic-tac-toe: 9-bit boards, bit = row*3 + col --------------------------------------------
