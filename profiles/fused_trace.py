@@ -12,6 +12,13 @@ if os.environ.get("LOGIT_SCALE"):  # sharpened priors: deeper trees (bench.py de
         model.policy.weight.mul_(float(os.environ["LOGIT_SCALE"]))
         model.policy.bias.mul_(float(os.environ["LOGIT_SCALE"]))
 me, opp, _ = env.reversi_init(B)
+if os.environ.get("PLIES"):  # mid-game roots: play lockstep self-play plies first (the bench region is plies 5-24)
+    from betazero_b200 import selfplay
+    sp = selfplay.BatchedSelfPlay(B, S, mcts.FusedNetEvaluator(model), temp_plies=8, seed=1234, n_leaves=4)
+    for _ in range(int(os.environ["PLIES"])):
+        sp.play_move()
+    me, opp = sp.me.clone(), sp.opp.clone()
+    del sp
 L = _lib.load()
 s = mcts.BatchedMCTS(mcts.TreePools(B, S, n_leaves=4), mcts.FusedNetEvaluator(model), use_graph=False)
 for _ in range(2):
