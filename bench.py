@@ -371,6 +371,18 @@ def run_b200(args):
                          "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": winst / (step_kernel_ms * 1e-3) / peak_issue}
         except Exception:
             pass
+        # third view of the same kernel when it contains the net (the one-launch search): the MLP's useful flops (one
+        # evaluation per simulation, 2 x (128 x 256 + 2 x 256 x 256 + 256 x 66) flop for the reference's architecture)
+        # against the measured dense bf16 peak
+        tensor_view = None
+        if one_launch and args.net == "mlp" and args.hidden == 256:
+            flop_per_leaf = 2 * (128 * 256 + 2 * 256 * 256 + 256 * 66)
+            tf = flop_per_leaf * sims_per_launch / (step_kernel_ms * 1e-3) / 1e12
+            tpeak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+            tensor_view = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tpeak else None,
+                           "flop_per_simulation": flop_per_leaf,
+                           "note": "useful MLP flops only (112 of the 128 rows of a tile are leaves; the head's 80-wide tile "
+                                   "counts as 66); peak = MEASURED_PEAKS.json sustained dense bf16"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -394,7 +406,7 @@ def run_b200(args):
                          "kernel_ms": step_kernel_ms, "kernel_ms_probe": probe_kind,
                          "net_kernel_ms": net_kernel_ms,
                          "bytes_per_sim": bytes_per_sim, "mean_depth": d, "mean_children": bmean,
-                         "sims_per_launch": sims_per_launch, "issue": issue, "static_note": static_note},
+                         "sims_per_launch": sims_per_launch, "issue": issue, "tensor": tensor_view, "static_note": static_note},
             "tree": {"mean_depth": d, "edges_per_sim": bmean, "pool_bytes": sp.pools.nbytes()},
             "selfplay": sp.stats(),
         }
